@@ -1,0 +1,132 @@
+"""Pins oracle/fourq_oracle.py to the golden vectors generated from the reference's own code
+(tests/golden/gen_golden.py).  CPU only."""
+import os
+
+import pytest
+
+from oracle import fourq_oracle as O
+
+H = bytes.fromhex
+
+
+def test_reference_selftests_all_passed():
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_selftest.txt")
+    lines = [l for l in open(path).read().splitlines() if l.strip()]
+    assert len(lines) == 64 and all(l.startswith("[PASS]") for l in lines)
+
+
+@pytest.mark.parametrize("op", ["mul", "add", "sub"])
+def test_fp2_binary(golden, op):
+    for a, b, out in golden["fields"][op]:
+        assert O.row_fp2(op, H(a), H(b)).hex() == out
+
+
+@pytest.mark.parametrize("op", ["sqr", "neg", "conj", "inv"])
+def test_fp2_unary(golden, op):
+    for a, out in golden["fields"][op]:
+        assert O.row_fp2(op, H(a)).hex() == out
+
+
+def test_fp_inv_invsqrt(golden):
+    for x, out in golden["fields"]["fp_inv"]:
+        assert O.fp_to_le(O.fp_inv(int.from_bytes(H(x), "little"))).hex() == out
+    for x, out in golden["fields"]["fp_invsqrt"]:
+        assert O.fp_to_le(O.fp_invsqrt(int.from_bytes(H(x), "little"))).hex() == out
+
+
+def test_encode_decode(golden):
+    c = golden["codec"]
+    assert O.encode(O.GX, O.GY).hex() == c["Genc"] == "87b2cb2b46a224b95a7820a19bee3f0e5c8b4c8444c3a74942020e63f84a1c6e"
+    for xy, enc in c["encode"]:
+        assert O.row_encode(H(xy)).hex() == enc
+    seen = set()
+    for enc, st, xy in c["decode"]:
+        got_xy, got_st = O.row_decode(H(enc))
+        assert (got_st, got_xy.hex()) == (st, xy), enc
+        seen.add(st)
+    assert seen == {0, 1, 2, 3, 4}
+
+
+def test_decode_does_not_mutate():
+    b = bytearray(H("87b2cb2b46a224b95a7820a19bee3f0e5c8b4c8444c3a74942020e63f84a1cee"))
+    keep = bytes(b)
+    O.decode_status(b)
+    assert bytes(b) == keep
+
+
+def test_mul_base(golden):
+    for k, out in golden["mul"]["mul_base"]:
+        assert O.row_mul_base(H(k)).hex() == out
+
+
+def test_dh_base(golden):
+    for k, st, out in golden["mul"]["dh_base"]:
+        got, gst = O.row_dh_base(H(k))
+        assert (gst, got.hex()) == (st, out)
+
+
+def test_dh_variable_base_both_algorithms(golden):
+    seen = set()
+    for i, (k, enc, st, out) in enumerate(golden["mul"]["dh"]):
+        got, gst = O.row_dh(H(k), H(enc))
+        assert (gst, got.hex()) == (st, out)
+        if i % 4 == 0:
+            got, gst = O.row_dh(H(k), H(enc), mul=O.mul_endo)
+            assert (gst, got.hex()) == (st, out)
+        seen.add(st)
+    assert seen == {0, 1, 2, 3, 4, 5}
+
+
+def test_dh_affine(golden):
+    for k, xy, st, out in golden["mul"]["dh_affine"]:
+        got, gst = O.row_dh_affine(H(k), H(xy))
+        assert (gst, got.hex()) == (st, out)
+
+
+def test_reference_kats(golden):
+    """curve4q.py:516-567: [2^1000]G, [1002]G-style chain and the 1000-step mulP chain."""
+    m = golden["mul"]
+    A = (O.GX, O.GY, O.F2_ONE)
+    for _ in range(1000):
+        A = O.dbl(A)[:3]
+    assert O.xy_to_bytes(O.r1_to_affine(A + (None, None))).hex() == m["doubleP_affine"]
+    P = O.affine_to_r1(O.GX, O.GY)
+    Q = O.r1_to_r2(P)
+    P = O.dbl(P[:3])
+    for _ in range(1000):
+        P = O.add(P, Q)
+    assert O.xy_to_bytes(O.r1_to_affine(P)).hex() == m["P1000_affine"]
+
+
+def test_mulP_chain_sample(golden):
+    """First 40 links of the chained KAT agree between windowed and endo; full chain is in the gpu tests."""
+    m = golden["mul"]
+    A = B = O.affine_to_r1(O.GX, O.GY)
+    for k in m["mulP_chain_scalars"][:40]:
+        A = O.mul_windowed(O.le_scalar(H(k)), A)
+        B = O.mul_endo(O.le_scalar(H(k)), B)
+    assert O.r1_to_affine(A) == O.r1_to_affine(B)
+
+
+def test_endo_pieces(golden):
+    e = golden["endo"]
+    for xy, out in e["phi"]:
+        P = O.xy_from_bytes(H(xy))
+        assert O.xy_to_bytes(O.r1_to_affine(O.phi(O.affine_to_r1(*P)))).hex() == out
+    for xy, out in e["psi"]:
+        P = O.xy_from_bytes(H(xy))
+        assert O.xy_to_bytes(O.r1_to_affine(O.psi(O.affine_to_r1(*P)))).hex() == out
+    for k, v in e["decompose"]:
+        assert O.decompose(O.le_scalar(H(k))) == v
+    for v, s, d in e["recode"]:
+        gs, gd = O.recode_endo(v)
+        assert "".join(map(str, gs)) == s and "".join(map(str, gd)) == d
+
+
+def test_x25519(golden):
+    for k, u, out in golden["x25519"]["x25519"]:
+        assert O.x25519(H(k), H(u)).hex() == out
+    # RFC 7748 5.2 vector, as in curve25519.py:97-102
+    assert O.x25519(H("a546e36bf0527c9d3b16154b82465edd62144c0ac1fc5a18506a2244ba449ac4"),
+                    H("e6db6867583030db3594c1a424b15f7c726624ec26b3353b10a903a6d0ab1c4c")).hex() == \
+        "c3da55379de9c6908e94ea4df28d084f32eccf03491c71f754b4075577a28552"
