@@ -15,12 +15,16 @@ typedef uint64_t u64;
 
 #ifdef FQ_HOSTSIM
 #define FQ_FN static inline
+#define FQ_MFN inline
 #define FQ_UNROLL
+#define FQ_NOUNROLL
 namespace fqsim { extern thread_local u32 cc; }
 #define FQ_CC (fqsim::cc)
 #else
 #define FQ_FN __device__ __forceinline__
+#define FQ_MFN __device__ __forceinline__
 #define FQ_UNROLL _Pragma("unroll")
+#define FQ_NOUNROLL _Pragma("unroll 1")
 #endif
 
 // ---------------------------------------------------------------- add / sub with carry

@@ -1,0 +1,130 @@
+// dh.cuh -- one thread = one scalar multiplication.  Table handling, the fixed-window main loop of MUL_windowed
+// (curve4q.py:188-235), and the Diffie-Hellman shell DH_core (curve4q.py:446-462).
+//
+// Table residency.  T[i] = [2i+1]P in R2 is 8 x 4 x 32 B = 1 KiB per thread.  Entries 0..6 live in shared memory as
+// 128-bit words laid out [entry][quad][thread] (consecutive threads -> consecutive 16 B: conflict-free LDS.128/STS.128),
+// entry 7 stays in registers: 7 x 128 B x 128 threads = 112 KiB per CTA, two CTAs per SM.
+// Selection reads ALL entries and keeps one with AND/OR masks (LOP3); the sign is applied with masks too.
+#pragma once
+#include "codec.cuh"
+#include "scalar.cuh"
+
+#ifdef FQ_HOSTSIM
+struct uint4 { u32 x, y, z, w; };
+FQ_FN uint4 make_uint4(u32 x, u32 y, u32 z, u32 w) { uint4 r = {x, y, z, w}; return r; }
+#endif
+
+// per-thread view of the shared-memory table: quad q of entry e is base[(e*8+q)*stride]
+struct TabView { uint4* base; u32 stride; };
+
+FQ_FN void tab_put(const TabView& T, int e, int q, const fp& a) { T.base[(e * 8 + q) * T.stride] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+FQ_FN fp tab_get(const TabView& T, int e, int q) { uint4 w = T.base[(e * 8 + q) * T.stride]; return fp_set(w.x, w.y, w.z, w.w); }
+
+FQ_FN void tab_store(const TabView& T, int e, const ptR2& P) {
+  tab_put(T, e, 0, P.N.re); tab_put(T, e, 1, P.N.im); tab_put(T, e, 2, P.D.re); tab_put(T, e, 3, P.D.im);
+  tab_put(T, e, 4, P.E.re); tab_put(T, e, 5, P.E.im); tab_put(T, e, 6, P.F.re); tab_put(T, e, 7, P.F.im);
+}
+FQ_FN ptR2 tab_load(const TabView& T, int e) {
+  ptR2 P;
+  P.N = fp2_set(tab_get(T, e, 0), tab_get(T, e, 1)); P.D = fp2_set(tab_get(T, e, 2), tab_get(T, e, 3));
+  P.E = fp2_set(tab_get(T, e, 4), tab_get(T, e, 5)); P.F = fp2_set(tab_get(T, e, 6), tab_get(T, e, 7));
+  return P;
+}
+
+FQ_FN void fp_or_masked(fp& acc, const fp& a, u32 m) {
+  acc.v[0] |= a.v[0] & m; acc.v[1] |= a.v[1] & m; acc.v[2] |= a.v[2] & m; acc.v[3] |= a.v[3] & m;
+}
+FQ_FN void r2_or_masked(ptR2& acc, const ptR2& a, u32 m) {
+  fp_or_masked(acc.N.re, a.N.re, m); fp_or_masked(acc.N.im, a.N.im, m); fp_or_masked(acc.D.re, a.D.re, m); fp_or_masked(acc.D.im, a.D.im, m);
+  fp_or_masked(acc.E.re, a.E.re, m); fp_or_masked(acc.E.im, a.E.im, m); fp_or_masked(acc.F.re, a.F.re, m); fp_or_masked(acc.F.im, a.F.im, m);
+}
+FQ_FN ptR2 r2_zero() { ptR2 P; P.N = fp2_zero(); P.D = fp2_zero(); P.E = fp2_zero(); P.F = fp2_zero(); return P; }
+
+// constant-time T[idx]: scan of entries 0..6 in shared memory plus the register-resident entry 7
+FQ_FN ptR2 tab_select(const TabView& T, const ptR2& T7, u32 idx) {
+  ptR2 S = r2_zero();
+  r2_or_masked(S, T7, (idx == 7) ? 0xffffffffu : 0u);
+  FQ_UNROLL
+  for (int e = 0; e < 7; e++) r2_or_masked(S, tab_load(T, e), (idx == (u32)e) ? 0xffffffffu : 0u);
+  return S;
+}
+
+// curve4q.py:179-185: T[i] = [2i+1]P, i = 0..7; returns T[7]
+FQ_FN ptR2 tab_build(const TabView& T, const ptR1& P) {
+  ptR1 P2 = P;
+  pt_dbl(P2);
+  ptR3p P2p = pt_r1_to_r3p(P2);
+  ptR2 Ti = pt_r1_to_r2(P);
+  tab_store(T, 0, Ti);
+  FQ_NOUNROLL
+  for (int i = 1; i < 8; i++) {
+    Ti = pt_r1_to_r2(pt_add_core(P2p, Ti));
+    if (i < 7) tab_store(T, i, Ti);
+  }
+  return Ti;
+}
+
+// curve4q.py:188-235 with the digits of scalar.cuh.  SELECT(idx) returns T[idx] in constant time.
+template <class SELECT> FQ_FN ptR1 mul_windowed(const scal& k, SELECT select) {
+  scal S = scal_digits_init(scal_reduce_odd(k));
+  ptR1 Q = pt_r2_to_r4(select(0u));                 // digit 62 is always +1
+  FQ_NOUNROLL
+  for (int i = 61; i >= 0; i--) {
+    FQ_NOUNROLL
+    for (int j = 0; j < 4; j++) pt_dbl(Q);
+    u32 idx, neg;
+    scal_next_digit(S, idx, neg);
+    Q = pt_add(Q, pt_r2_cneg(neg, select(idx)));
+  }
+  return Q;
+}
+
+struct SelectShared {
+  TabView T; ptR2 T7;
+  FQ_MFN ptR2 operator()(u32 idx) const { return tab_select(T, T7, idx); }
+};
+
+// DH_core (curve4q.py:446-462) after the point has been validated: [392]P, table, [k]Q, affine, neutral check.
+FQ_FN u32 dh_variable_base(const scal& k, const fp2& x, const fp2& y, const TabView& T, fp2& ox, fp2& oy) {
+  ptR1 Q = pt_clear_cofactor(x, y);
+  SelectShared sel; sel.T = T;
+  sel.T7 = tab_build(T, Q);
+  ptR1 R = mul_windowed(k, sel);
+  pt_to_affine(R, ox, oy);
+  bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());      // curve4q.py:459
+  return neutral ? FQ_ST_NEUTRAL : FQ_ST_OK;
+}
+
+// fixed base: the table is read-only, shared by all threads (constant bank), 8 entries x 32 words
+struct SelectConst {
+  const u32* tab;   // [8][32], entry layout N.re N.im D.re D.im E.re E.im F.re F.im
+  FQ_MFN ptR2 operator()(u32 idx) const {
+    u32 w[32];
+    FQ_UNROLL
+    for (int j = 0; j < 32; j++) w[j] = 0;
+    FQ_UNROLL
+    for (int e = 0; e < 8; e++) {
+      u32 m = (idx == (u32)e) ? 0xffffffffu : 0u;
+      FQ_UNROLL
+      for (int j = 0; j < 32; j++) w[j] |= tab[e * 32 + j] & m;
+    }
+    ptR2 P;
+    P.N = fp2_set(fp_set(w[0], w[1], w[2], w[3]), fp_set(w[4], w[5], w[6], w[7]));
+    P.D = fp2_set(fp_set(w[8], w[9], w[10], w[11]), fp_set(w[12], w[13], w[14], w[15]));
+    P.E = fp2_set(fp_set(w[16], w[17], w[18], w[19]), fp_set(w[20], w[21], w[22], w[23]));
+    P.F = fp2_set(fp_set(w[24], w[25], w[26], w[27]), fp_set(w[28], w[29], w[30], w[31]));
+    return P;
+  }
+};
+FQ_FN void r2_to_words(const ptR2& P, u32* w) {
+  const fp* f[8] = {&P.N.re, &P.N.im, &P.D.re, &P.D.im, &P.E.re, &P.E.im, &P.F.re, &P.F.im};
+  FQ_UNROLL
+  for (int q = 0; q < 8; q++) { FQ_UNROLL for (int j = 0; j < 4; j++) w[q * 4 + j] = f[q]->v[j]; }
+}
+
+// [k]B for the base point whose table is `tab`; returns canonical affine.  MUL_windowed(k, ., table) + R1toAffine.
+FQ_FN void mul_fixed_base(const scal& k, const u32* tab, fp2& ox, fp2& oy) {
+  SelectConst sel; sel.tab = tab;
+  ptR1 R = mul_windowed(k, sel);
+  pt_to_affine(R, ox, oy);
+}

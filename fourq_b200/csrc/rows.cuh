@@ -1,0 +1,90 @@
+// rows.cuh -- what each batched entry point computes for ONE row, on register-resident words.
+// Shared by the CUDA kernels (kernels.cu) and by the CPU instruction-level simulation used in tests/hostsim.
+// Byte conventions (include/fourq_b200.h): GF(p^2) element = LE128(re)|LE128(im); affine point = x|y (64 B);
+// encoded point and scalar = 32 B.  Words are the little-endian u32 view of those bytes.
+#pragma once
+#include "dh.cuh"
+
+// any two 128-bit values -> tight GF(p^2) element (the reference's ops accept unreduced ints: fields.py:157-181)
+FQ_FN fp2 row_load_fp2(const u32* w) {
+  return fp2_set(fp_from_u128(fp_set(w[0], w[1], w[2], w[3])), fp_from_u128(fp_set(w[4], w[5], w[6], w[7])));
+}
+FQ_FN void row_store_fp2(u32* w, const fp2& a) {
+  fp2 c = fp2_canon(a);
+  FQ_UNROLL
+  for (int i = 0; i < 4; i++) { w[i] = c.re.v[i]; w[4 + i] = c.im.v[i]; }
+}
+FQ_FN scal row_load_scalar(const u32* w) {
+  scal k;
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) k.v[i] = w[i];
+  return k;
+}
+
+enum { FQ_OP_MUL = 0, FQ_OP_SQR = 1, FQ_OP_INV = 2, FQ_OP_ADD = 3, FQ_OP_SUB = 4, FQ_OP_NEG = 5, FQ_OP_CONJ = 6 };
+
+template <int OP> FQ_FN void row_fp2_op(const u32* a, const u32* b, u32* out) {
+  fp2 x = row_load_fp2(a), r;
+  if (OP == FQ_OP_MUL) r = fp2_mul(x, row_load_fp2(b));
+  else if (OP == FQ_OP_ADD) r = fp2_add(x, row_load_fp2(b));
+  else if (OP == FQ_OP_SUB) r = fp2_sub(x, row_load_fp2(b));
+  else if (OP == FQ_OP_SQR) r = fp2_sqr(x);
+  else if (OP == FQ_OP_INV) r = fp2_inv(x);
+  else if (OP == FQ_OP_NEG) r = fp2_neg(x);
+  else r = fp2_conj(x);
+  row_store_fp2(out, r);
+}
+
+// decode: 8 words -> 16 words (x0|x1|y0|y1), zero-filled on failure
+FQ_FN u32 row_decode(const u32* enc, u32* xy) {
+  fp2 x, y;
+  u32 st = pt_decode(enc, x, y);
+  if (st != FQ_ST_OK) { x = fp2_zero(); y = fp2_zero(); }
+  row_store_fp2(xy, x); row_store_fp2(xy + 8, y);
+  return st;
+}
+// encode: 16 words -> 8 words.  Coordinates are reduced mod p first.
+FQ_FN void row_encode(const u32* xy, u32* enc) {
+  fp2 x = fp2_canon(row_load_fp2(xy)), y = fp2_canon(row_load_fp2(xy + 8));
+  pt_encode(x, y, enc);
+}
+
+FQ_FN void row_zero(u32* w, int n) { for (int i = 0; i < n; i++) w[i] = 0; }
+
+// fq_dh: decode(enc) -> DH_windowed -> encode
+FQ_FN u32 row_dh(const u32* k, const u32* enc, u32* out, const TabView& T) {
+  fp2 x, y, ox, oy;
+  u32 st = pt_decode(enc, x, y);
+  if (st == FQ_ST_OK) st = dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
+  if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);
+  return st;
+}
+// fq_dh_affine: DH_windowed on an affine point (64 B in, 64 B out)
+FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* out, const TabView& T) {
+  fp2 x = fp2_canon(row_load_fp2(xy)), y = fp2_canon(row_load_fp2(xy + 8)), ox, oy;
+  u32 st = pt_on_curve(x, y) ? FQ_ST_OK : FQ_ST_NOT_ON_CURVE;                       // curve4q.py:447
+  if (st == FQ_ST_OK) st = dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
+  if (st == FQ_ST_OK) { row_store_fp2(out, ox); row_store_fp2(out + 8, oy); } else row_zero(out, 16);
+  return st;
+}
+// fq_mul_base (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base (true): encode([k][392]G) with the neutral check
+template <bool CHECK_NEUTRAL> FQ_FN u32 row_fixed_base(const u32* k, const u32* tab, u32* out) {
+  fp2 ox, oy;
+  mul_fixed_base(row_load_scalar(k), tab, ox, oy);
+  u32 st = FQ_ST_OK;
+  if (CHECK_NEUTRAL && (fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one()))) st = FQ_ST_NEUTRAL;
+  if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);
+  return st;
+}
+
+// Fixed-base tables: out[0..255] = table_windowed(G) (curve4q.py:582), out[256..511] = table_windowed([392]G)
+// (curve4q.py:758-759).  scratch: 56 uint4.
+FQ_FN void row_build_base_tables(u32* out, uint4* scratch) {
+  TabView T; T.base = scratch; T.stride = 1;
+  for (int which = 0; which < 2; which++) {
+    ptR1 B = (which == 0) ? pt_from_affine(curve_gx(), curve_gy()) : pt_clear_cofactor(curve_gx(), curve_gy());
+    ptR2 T7 = tab_build(T, B);
+    for (int e = 0; e < 7; e++) { ptR2 P = tab_load(T, e); r2_to_words(P, out + which * 256 + e * 32); }
+    r2_to_words(T7, out + which * 256 + 7 * 32);
+  }
+}

@@ -1,0 +1,105 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles the device headers of fourq_b200/csrc with -DFQ_HOSTSIM, where every
+// PTX primitive of arith.cuh is emulated instruction by instruction (including the carry flag), and exposes the per-row
+// routines of rows.cuh to the CPU tests.  This lets `pytest -m "not gpu"` check the exact limb-level algorithms against
+// the golden vectors without a GPU.  It is NOT linked into, loaded by, or a fallback for libfourq_b200.so.
+#define FQ_HOSTSIM 1
+#include <cstring>
+#include <cstddef>
+#include "../../fourq_b200/csrc/rows.cuh"
+
+namespace fqsim { thread_local u32 cc = 0; }
+
+static u32 g_tabs[512];
+static bool g_tabs_ready = false;
+static void ensure_tabs() {
+  if (!g_tabs_ready) { uint4 scratch[56]; row_build_base_tables(g_tabs, scratch); g_tabs_ready = true; }
+}
+
+extern "C" {
+
+int sim_fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wa[8], wb[8] = {0}, wo[8];
+    memcpy(wa, a + 32 * i, 32);
+    if (b) memcpy(wb, b + 32 * i, 32);
+    switch (op) {
+      case FQ_OP_MUL: row_fp2_op<FQ_OP_MUL>(wa, wb, wo); break;
+      case FQ_OP_SQR: row_fp2_op<FQ_OP_SQR>(wa, wb, wo); break;
+      case FQ_OP_INV: row_fp2_op<FQ_OP_INV>(wa, wb, wo); break;
+      case FQ_OP_ADD: row_fp2_op<FQ_OP_ADD>(wa, wb, wo); break;
+      case FQ_OP_SUB: row_fp2_op<FQ_OP_SUB>(wa, wb, wo); break;
+      case FQ_OP_NEG: row_fp2_op<FQ_OP_NEG>(wa, wb, wo); break;
+      case FQ_OP_CONJ: row_fp2_op<FQ_OP_CONJ>(wa, wb, wo); break;
+      default: return -1;
+    }
+    memcpy(out + 32 * i, wo, 32);
+  }
+  return 0;
+}
+
+// which: 0 = inv, 1 = invsqrt, 2 = dbl, 3 = half; 16-byte rows, input tight
+int sim_fp_op(int which, const uint8_t* a, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 w[4]; memcpy(w, a + 16 * i, 16);
+    fp x = fp_from_u128(fp_set(w[0], w[1], w[2], w[3]));
+    fp r = which == 0 ? fp_inv(x) : which == 1 ? fp_invsqrt(x) : which == 2 ? fp_dbl(x) : fp_half(x);
+    r = fp_canon(r);
+    memcpy(out + 16 * i, r.v, 16);
+  }
+  return 0;
+}
+
+int sim_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 we[8], wo[16]; memcpy(we, enc + 32 * i, 32);
+    status[i] = (uint8_t)row_decode(we, wo);
+    memcpy(xy + 64 * i, wo, 64);
+  }
+  return 0;
+}
+int sim_encode(const uint8_t* xy, uint8_t* enc, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wi[16], wo[8]; memcpy(wi, xy + 64 * i, 64);
+    row_encode(wi, wo);
+    memcpy(enc + 32 * i, wo, 32);
+  }
+  return 0;
+}
+int sim_dh(const uint8_t* k, const uint8_t* enc, uint8_t* out, uint8_t* status, size_t n) {
+  uint4 tab[56]; TabView T; T.base = tab; T.stride = 1;
+  for (size_t i = 0; i < n; i++) {
+    u32 wk[8], we[8], wo[8]; memcpy(wk, k + 32 * i, 32); memcpy(we, enc + 32 * i, 32);
+    status[i] = (uint8_t)row_dh(wk, we, wo, T);
+    memcpy(out + 32 * i, wo, 32);
+  }
+  return 0;
+}
+int sim_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* out, uint8_t* status, size_t n) {
+  uint4 tab[56]; TabView T; T.base = tab; T.stride = 1;
+  for (size_t i = 0; i < n; i++) {
+    u32 wk[8], wi[16], wo[16]; memcpy(wk, k + 32 * i, 32); memcpy(wi, xy + 64 * i, 64);
+    status[i] = (uint8_t)row_dh_affine(wk, wi, wo, T);
+    memcpy(out + 64 * i, wo, 64);
+  }
+  return 0;
+}
+int sim_fixed_base(int dh, const uint8_t* k, uint8_t* out, uint8_t* status, size_t n) {
+  ensure_tabs();
+  for (size_t i = 0; i < n; i++) {
+    u32 wk[8], wo[8]; memcpy(wk, k + 32 * i, 32);
+    u32 st = dh ? row_fixed_base<true>(wk, g_tabs + 256, wo) : row_fixed_base<false>(wk, g_tabs, wo);
+    if (status) status[i] = (uint8_t)st;
+    memcpy(out + 32 * i, wo, 32);
+  }
+  return 0;
+}
+// digits of the recoding: idx[62], neg[62] for i = 61..0 (in pop order), plus the reduced odd scalar (32 bytes)
+int sim_recode(const uint8_t* k, uint8_t* idx, uint8_t* neg, uint8_t* reduced) {
+  u32 wk[8]; memcpy(wk, k, 32);
+  scal r = scal_reduce_odd(row_load_scalar(wk));
+  memcpy(reduced, r.v, 32);
+  scal S = scal_digits_init(r);
+  for (int i = 0; i < 62; i++) { u32 a, b; scal_next_digit(S, a, b); idx[i] = (uint8_t)a; neg[i] = (uint8_t)(b & 1); }
+  return 0;
+}
+}  // extern "C"

@@ -1,0 +1,152 @@
+"""CPU checks of the DEVICE algorithms (fourq_b200/csrc/*.cuh) through tests/hostsim: the same headers compiled with
+-DFQ_HOSTSIM, every PTX primitive emulated with its carry flag.  Compared with the golden vectors generated from the
+reference and with the oracle on seeded random and edge inputs.  Test infrastructure only (the product has no CPU path)."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import fourq_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+H = bytes.fromhex
+OPS = {"mul": 0, "sqr": 1, "inv": 2, "add": 3, "sub": 4, "neg": 5, "conj": 6}
+
+
+@pytest.fixture(scope="module")
+def sim():
+    so = os.path.join(HERE, "hostsim", "libfq_hostsim.so")
+    srcs = [os.path.join(HERE, "hostsim", "hostsim.cpp")] + [
+        os.path.join(HERE, "..", "fourq_b200", "csrc", f) for f in os.listdir(os.path.join(HERE, "..", "fourq_b200", "csrc")) if f.endswith(".cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call([os.path.join(HERE, "hostsim", "build.sh")])
+    return ctypes.CDLL(so)
+
+
+def _rows(lst):
+    return np.frombuffer(b"".join(lst), dtype=np.uint8).copy()
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def fp2_op(sim, op, A, B=None):
+    a = _rows(A); out = np.zeros_like(a)
+    b = _rows(B) if B is not None else None
+    assert sim.sim_fp2_op(OPS[op], _p(a), _p(b) if b is not None else None, _p(out), ctypes.c_size_t(len(A))) == 0
+    return [bytes(out[32 * i:32 * i + 32]) for i in range(len(A))]
+
+
+@pytest.mark.parametrize("op", ["mul", "add", "sub"])
+def test_fp2_binary_golden(sim, golden, op):
+    rows = golden["fields"][op]
+    got = fp2_op(sim, op, [H(r[0]) for r in rows], [H(r[1]) for r in rows])
+    assert [g.hex() for g in got] == [r[2] for r in rows]
+
+
+@pytest.mark.parametrize("op", ["sqr", "neg", "conj", "inv"])
+def test_fp2_unary_golden(sim, golden, op):
+    rows = golden["fields"][op]
+    got = fp2_op(sim, op, [H(r[0]) for r in rows])
+    assert [g.hex() for g in got] == [r[1] for r in rows]
+
+
+def test_fp2_random_and_adversarial_vs_oracle(sim):
+    rng = random.Random(7)
+    p = O.P127
+    special = [0, 1, 2, p - 1, p, p - 2, 1 << 126, (1 << 126) - 1, (1 << 64) - 1, (1 << 64) + 1, (1 << 96) - 1, 0xFFFFFFFF,
+               (1 << 127) - (1 << 32), (1 << 127) - (1 << 64) - 1, 0xFFFFFFFF00000000FFFFFFFF00000000, 0x7FFFFFFF00000000FFFFFFFFFFFFFFFF]
+    vals = special + [rng.getrandbits(127) for _ in range(64)]
+    # limb patterns that maximise carries
+    vals += [int.from_bytes(bytes(rng.choice([0, 0xFF]) for _ in range(16)), "little") & p for _ in range(64)]
+    A = []; B = []
+    for _ in range(4000):
+        a = (rng.choice(vals), rng.choice(vals)); b = (rng.choice(vals), rng.choice(vals))
+        A.append(O.f2_to_bytes_raw(a) if hasattr(O, "f2_to_bytes_raw") else (a[0].to_bytes(16, "little") + a[1].to_bytes(16, "little")))
+        B.append(b[0].to_bytes(16, "little") + b[1].to_bytes(16, "little"))
+    for op in ("mul", "add", "sub"):
+        got = fp2_op(sim, op, A, B)
+        for a, b, g in zip(A, B, got):
+            assert g == O.row_fp2(op, a, b), (op, a.hex(), b.hex())
+    for op in ("sqr", "neg", "conj"):
+        got = fp2_op(sim, op, A)
+        for a, g in zip(A, got):
+            assert g == O.row_fp2(op, a), (op, a.hex())
+    got = fp2_op(sim, "inv", A[:300])
+    for a, g in zip(A[:300], got):
+        assert g == O.row_fp2("inv", a)
+
+
+def test_fp_inv_invsqrt_dbl_half(sim, golden):
+    for which, key in ((0, "fp_inv"), (1, "fp_invsqrt")):
+        rows = golden["fields"][key]
+        a = _rows([H(r[0]) for r in rows]); out = np.zeros_like(a)
+        sim.sim_fp_op(which, _p(a), _p(out), ctypes.c_size_t(len(rows)))
+        assert [bytes(out[16 * i:16 * i + 16]).hex() for i in range(len(rows))] == [r[1] for r in rows]
+    rng = random.Random(3)
+    xs = [0, 1, O.P127 - 1, O.P127, 1 << 126] + [rng.getrandbits(127) for _ in range(200)]
+    a = _rows([x.to_bytes(16, "little") for x in xs])
+    for which, f in ((2, lambda x: 2 * x % O.P127), (3, lambda x: x * (1 << 126) % O.P127)):
+        out = np.zeros_like(a)
+        sim.sim_fp_op(which, _p(a), _p(out), ctypes.c_size_t(len(xs)))
+        assert [int.from_bytes(bytes(out[16 * i:16 * i + 16]), "little") for i in range(len(xs))] == [f(x) for x in xs]
+
+
+def test_codec_golden(sim, golden):
+    c = golden["codec"]
+    xy = _rows([H(r[0]) for r in c["encode"]]); enc = np.zeros(32 * len(c["encode"]), np.uint8)
+    sim.sim_encode(_p(xy), _p(enc), ctypes.c_size_t(len(c["encode"])))
+    assert [bytes(enc[32 * i:32 * i + 32]).hex() for i in range(len(c["encode"]))] == [r[1] for r in c["encode"]]
+    e = _rows([H(r[0]) for r in c["decode"]]); n = len(c["decode"])
+    out = np.zeros(64 * n, np.uint8); st = np.zeros(n, np.uint8)
+    sim.sim_decode(_p(e), _p(out), _p(st), ctypes.c_size_t(n))
+    for i, (enc_hex, want_st, want_xy) in enumerate(c["decode"]):
+        assert (int(st[i]), bytes(out[64 * i:64 * i + 64]).hex()) == (want_st, want_xy), enc_hex
+
+
+def test_recode_matches_reference_digits(sim):
+    rng = random.Random(11)
+    ks = [0, 1, 2, O.N - 1, O.N, O.N + 1, 2 * O.N, (1 << 256) - 1, ((1 << 256) // O.N) * O.N, ((1 << 256) // O.N) * O.N - 1]
+    ks += [rng.getrandbits(256) for _ in range(2000)] + [rng.getrandbits(32) << 224 | rng.getrandbits(8) for _ in range(500)]
+    for k in ks:
+        kb = np.frombuffer(k.to_bytes(32, "little"), np.uint8).copy()
+        idx = np.zeros(62, np.uint8); neg = np.zeros(62, np.uint8); red = np.zeros(32, np.uint8)
+        sim.sim_recode(_p(kb), _p(idx), _p(neg), _p(red))
+        ind, sgn = O.recode_windowed(k)
+        r = k % O.N
+        r += O.N if r % 2 == 0 else 0
+        assert int.from_bytes(bytes(red), "little") == r
+        assert ind[62] == 0 and sgn[62] == 1
+        assert list(idx) == [ind[i] for i in range(61, -1, -1)]
+        assert list(neg) == [1 - sgn[i] for i in range(61, -1, -1)]
+
+
+def test_fixed_base_golden(sim, golden):
+    rows = golden["mul"]["mul_base"]
+    k = _rows([H(r[0]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8)
+    sim.sim_fixed_base(0, _p(k), _p(out), None, ctypes.c_size_t(len(rows)))
+    assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[1] for r in rows]
+    rows = golden["mul"]["dh_base"]
+    k = _rows([H(r[0]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8); st = np.zeros(len(rows), np.uint8)
+    sim.sim_fixed_base(1, _p(k), _p(out), _p(st), ctypes.c_size_t(len(rows)))
+    for i, (kk, want_st, want) in enumerate(rows):
+        assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), kk
+
+
+def test_dh_golden(sim, golden):
+    rows = golden["mul"]["dh"]
+    k = _rows([H(r[0]) for r in rows]); e = _rows([H(r[1]) for r in rows]); n = len(rows)
+    out = np.zeros(32 * n, np.uint8); st = np.zeros(n, np.uint8)
+    sim.sim_dh(_p(k), _p(e), _p(out), _p(st), ctypes.c_size_t(n))
+    for i, (kk, ee, want_st, want) in enumerate(rows):
+        assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), (kk, ee)
+    rows = golden["mul"]["dh_affine"]
+    k = _rows([H(r[0]) for r in rows]); xy = _rows([H(r[1]) for r in rows]); n = len(rows)
+    out = np.zeros(64 * n, np.uint8); st = np.zeros(n, np.uint8)
+    sim.sim_dh_affine(_p(k), _p(xy), _p(out), _p(st), ctypes.c_size_t(n))
+    for i, (kk, pp, want_st, want) in enumerate(rows):
+        assert (int(st[i]), bytes(out[64 * i:64 * i + 64]).hex()) == (want_st, want), (kk, pp)
