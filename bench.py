@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of fourq_b200: Curve4Q scalar multiplications per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1, one rank per GPU)
+
+Workload (config.workload): BASELINE.json configs[2] -- variable-base DH, 2^20 (scalar, encoded point) rows per GPU:
+decode + validate + cofactor clearing + fixed-window scalar multiplication + inversion + encode, one kernel launch per
+step.  Every row is independent, so N GPUs run N independent slices (weak scaling, no collective on the data path;
+torch.distributed is used only for the barrier and the max-over-ranks of the timings).
+
+One JSON line is printed by rank 0:
+  value      rows/s with inputs resident in HBM, CUDA-event time of the kernel, L2 flushed between steps
+  e2e        the same rows through the public API fourq_b200.DH() from pinned host numpy arrays (H2D + kernels + D2H)
+  roofline   achieved = value x 103,836 algorithmic 32x32->64 multiply-adds per row ("tight" count of
+             decode + DH_windowed + encode) against the IMAD.WIDE.U32 issue peak measured live on the same GPU
+  cpu_baseline  the oracle (Python restatement of the reference) on the host's cores over a bounded sample; the same
+             sample is compared bit-for-bit with the GPU output
+--impl reference times the reference's CPU algorithm (the oracle port: the reference itself is Python 2 and cannot run
+here) with multiprocessing on all host cores, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "curve4q_variable_base_dh_scalar_mults_per_s"
+UNIT = "scalar-mults/s"
+ROWS_PER_GPU = 1 << 20
+IMADS_PER_ROW = 103836          # cfg 3 decode + DH_windowed + encode, tight count
+BYTES_PER_ROW = 96              # 32 scalar + 32 point + 32 out
+WORKLOAD = "cfg3 variable-base DH (decode+validate+[392]P+fixed-window [k]Q+inversion+encode), 2^20 (scalar, encoded point) rows per GPU"
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous slice [lo, hi) of n rows owned by `rank` (same rule as the C ABI: ceil(n/world) rows per slice)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def make_inputs(fq, rows, rank):
+    """Seeded synthetic inputs (SURVEY.md 8d cfg 3): uniform scalars; public keys = [k']G for uniform k' (valid points)."""
+    k = np.random.default_rng(3 + 1000 * rank).integers(0, 256, (rows, 32), np.uint8)
+    kp = np.random.default_rng(4 + 1000 * rank).integers(0, 256, (rows, 32), np.uint8)
+    pub = fq.MUL_base(kp)
+    return k, pub
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- CPU arm (oracle port of the reference)
+
+def _cpu_row(args):
+    from oracle import fourq_oracle as O
+    return O.row_dh(args[0], args[1])
+
+
+def cpu_dh(k, pub, procs):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_row, [(bytes(k[i]), bytes(pub[i])) for i in range(len(k))], chunksize=max(1, len(k) // (procs * 8)))
+        dt = time.perf_counter() - t0
+    return res, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 128 * cores
+    # inputs for the CPU arm are generated on the CPU (valid points from the oracle's own fixed-base multiplication)
+    from oracle import fourq_oracle as O
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, 256, (sample, 32), np.uint8)
+    base = [O.row_mul_base(bytes(r)) for r in np.random.default_rng(4).integers(0, 256, (16, 32), np.uint8)]
+    pub = np.frombuffer(b"".join(base[i % 16] for i in range(sample)), np.uint8).reshape(sample, 32)
+    for _ in range(args.warmup):
+        cpu_dh(k[: 8 * cores], pub[: 8 * cores], cores)
+    total = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_dh(k, pub, cores)
+        total += dt
+    value = sample * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_rows_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d rows per step x %d steps, oracle/fourq_oracle.py row_dh under multiprocessing" % (sample, args.steps)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- GPU arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default 2^20, the BASELINE size)")
+    ap.add_argument("--cpu-sample", type=int, default=-1, help="rows of the CPU baseline sample (default 256 per core; 0 = skip)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import fourq_b200 as fq
+    from fourq_b200 import device as fqdev
+    fq.set_device(local_rank)
+    rows = args.rows
+    k, pub = make_inputs(fq, rows, rank)
+
+    # ---- device-resident arm: `value`
+    dk = fqdev.DeviceBuffer.from_host(local_rank, k)
+    dp = fqdev.DeviceBuffer.from_host(local_rank, pub)
+    dout = fqdev.DeviceBuffer(local_rank, rows * 32)
+    dst = fqdev.DeviceBuffer(local_rank, rows)
+    for _ in range(args.warmup):
+        fqdev.dev_run("dh", local_rank, dk, dp, dout, dst, rows)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    kernel_ms = []
+    for _ in range(args.steps):
+        fqdev.flush_l2(local_rank)                       # untimed: write 256 MiB > L2 between timed iterations
+        kernel_ms.append(fqdev.dev_run("dh", local_rank, dk, dp, dout, dst, rows))   # CUDA events on the launch stream
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(sum(kernel_ms))
+    value = world * rows * args.steps / (total_ms * 1e-3)
+    out_dev = dout.to_host((rows, 32))
+    st_dev = dst.to_host((rows,))
+
+    # ---- end-to-end arm through the public API from pinned host memory: `e2e`
+    pk = fq.pinned_empty((rows, 32)); pk[:] = k
+    pp = fq.pinned_empty((rows, 32)); pp[:] = pub
+    for _ in range(2):
+        fq.DH(pk, pp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_e2e, st_e2e = fq.DH(pk, pp)                  # H2D of k and pub, kernels, D2H of out and status: every step
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * rows * args.steps / e2e_s
+    assert (out_e2e == out_dev).all() and (st_e2e == st_dev).all() and not st_dev.any()
+
+    # ---- roofline denominator measured live + CPU baseline and parity on a sample (rank 0)
+    line = None
+    if rank == 0:
+        wide_peak, imad_peak = fqdev.imad_peak(local_rank)
+        achieved = (value / world) * IMADS_PER_ROW
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "imad", "achieved": achieved / 1e12, "peak": wide_peak / 1e12, "unit": "T IMAD.WIDE/s", "frac": achieved / wide_peak,
+                    "traffic": None,
+                    "note": "per GPU; achieved = rows/s x %d algorithmic 32x32->64 multiply-adds per row (SURVEY 8d); peak = IMAD.WIDE.U32 "
+                            "issue rate measured live by fq_imad_peak (32-bit IMAD measured %.2f T/s); HBM is not the bound: "
+                            "%d B/row -> %.4f of %s %.1f GB/s" % (IMADS_PER_ROW, imad_peak / 1e12, BYTES_PER_ROW,
+                                                                   (value / world) * BYTES_PER_ROW / 1e9 / hbm,
+                                                                   "measured" if peaks else "fallback", hbm)}
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample if args.cpu_sample >= 0 else 256 * cores
+        cpu = None
+        if sample > 0:
+            sample = min(sample, rows)
+            res, dt = cpu_dh(k[:sample], pub[:sample], cores)
+            got = [(bytes(out_dev[i]), int(st_dev[i])) for i in range(sample)]
+            if got != res:
+                raise SystemExit("PARITY FAILURE: GPU output differs from the oracle on the CPU-baseline sample")
+            cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "first %d rows of rank 0's batch, oracle row_dh under multiprocessing (%d procs); bit-exact with the GPU rows" % (sample, cores)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rows_per_gpu": rows, "l2": "flushed (256 MiB memset) between timed iterations",
+                           "timing": "CUDA events around each kernel launch, summed over steps, max over ranks", "wall_s_timed_region": wall},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * rows, "d2h_bytes_per_step": 33 * rows,
+                        "note": "fourq_b200.DH(k, B) on pinned numpy arrays, wall clock, per GPU bytes"},
+                "gpu_launches": args.steps,
+                "roofline": roofline, "cpu_baseline": cpu}
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,308 @@
+// capi.cu -- the C ABI of include/fourq_b200.h and the host engine behind it.
+//
+// Host engine.  A call splits its rows into contiguous per-GPU slices (every row is independent, there
+// is no exchange step, hence no collective).  Each GPU runs its slice as a software pipeline of chunks over three
+// CUDA streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.  Chunks of all devices are
+// enqueued round-robin before anything is waited on.  Device staging buffers are kept per (device, stream) and
+// grow on demand; nothing else is cached between calls.  There is no CPU implementation of any operation here.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/fourq_b200.h"
+#include "kernels.h"
+
+namespace {
+
+constexpr int kStreams = 3;
+constexpr int kMaxDev = 16;
+constexpr size_t kFlushBytes = 256u << 20;      // > 126 MB L2
+
+thread_local char tl_err[512] = "";
+thread_local float tl_kernel_ms = 0.f;
+std::mutex g_mu;
+int g_dev_base = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(tl_err, sizeof(tl_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                       \
+  do { cudaError_t e_ = (call);                                                                        \
+       if (e_ != cudaSuccess) return fail(FQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct Slot { void* buf[4] = {nullptr, nullptr, nullptr, nullptr}; size_t cap[4] = {0, 0, 0, 0}; };
+struct DevCtx {
+  bool ready = false;
+  cudaStream_t st[kStreams];
+  Slot slot[kStreams];
+  void* flush = nullptr;
+};
+DevCtx g_ctx[kMaxDev];
+
+int device_count() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(FQ_ERR_NO_DEVICE, "no CUDA device available (%s); fourq_b200 has no CPU path", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)); }
+  return n > kMaxDev ? kMaxDev : n;
+}
+
+int ctx_init(int dev) {
+  DevCtx& c = g_ctx[dev];
+  CU(cudaSetDevice(dev));
+  if (c.ready) return FQ_OK;
+  for (int i = 0; i < kStreams; i++) CU(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
+  CU(fqk_device_init(c.st[0]));
+  c.ready = true;
+  return FQ_OK;
+}
+
+int slot_reserve(Slot& s, int which, size_t bytes) {
+  if (bytes <= s.cap[which]) return FQ_OK;
+  if (s.buf[which]) CU(cudaFree(s.buf[which]));
+  s.buf[which] = nullptr; s.cap[which] = 0;
+  CU(cudaMalloc(&s.buf[which], bytes));
+  s.cap[which] = bytes;
+  return FQ_OK;
+}
+
+// bytes per row of each operand of an operation
+struct OpDesc { int op; int a_bytes, b_bytes, out_bytes; bool status; size_t chunk_rows; };
+
+OpDesc describe(int op) {
+  switch (op) {
+    case FQ_DEVOP_FP2_MUL: case FQ_DEVOP_FP2_ADD: case FQ_DEVOP_FP2_SUB: return {op, 32, 32, 32, false, (size_t)1 << 20};
+    case FQ_DEVOP_FP2_SQR: case FQ_DEVOP_FP2_NEG: case FQ_DEVOP_FP2_CONJ: return {op, 32, 0, 32, false, (size_t)1 << 20};
+    case FQ_DEVOP_FP2_INV: return {op, 32, 0, 32, false, (size_t)1 << 18};
+    case FQ_DEVOP_DECODE: return {op, 32, 0, 64, true, (size_t)1 << 18};
+    case FQ_DEVOP_ENCODE: return {op, 64, 0, 32, false, (size_t)1 << 20};
+    case FQ_DEVOP_DH: return {op, 32, 32, 32, true, (size_t)1 << 17};
+    case FQ_DEVOP_DH_AFFINE: return {op, 32, 64, 64, true, (size_t)1 << 17};
+    case FQ_DEVOP_DH_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
+    case FQ_DEVOP_MUL_BASE: return {op, 32, 0, 32, false, (size_t)1 << 17};
+    case FQ_DEVOP_X25519: return {op, 32, 32, 32, false, (size_t)1 << 17};
+    default: return {-1, 0, 0, 0, false, 0};
+  }
+}
+
+cudaError_t launch(int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s) {
+  switch (op) {
+    case FQ_DEVOP_FP2_MUL: return fqk_fp2_op(FQK_MUL, a, b, out, n, s);
+    case FQ_DEVOP_FP2_SQR: return fqk_fp2_op(FQK_SQR, a, b, out, n, s);
+    case FQ_DEVOP_FP2_INV: return fqk_fp2_op(FQK_INV, a, b, out, n, s);
+    case FQ_DEVOP_FP2_ADD: return fqk_fp2_op(FQK_ADD, a, b, out, n, s);
+    case FQ_DEVOP_FP2_SUB: return fqk_fp2_op(FQK_SUB, a, b, out, n, s);
+    case FQ_DEVOP_FP2_NEG: return fqk_fp2_op(FQK_NEG, a, b, out, n, s);
+    case FQ_DEVOP_FP2_CONJ: return fqk_fp2_op(FQK_CONJ, a, b, out, n, s);
+    case FQ_DEVOP_DECODE: return fqk_decode(a, out, status, n, s);
+    case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
+    case FQ_DEVOP_DH: return fqk_dh(0, a, b, out, status, n, s);
+    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, a, b, out, status, n, s);
+    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, a, out, status, n, s);
+    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, a, out, nullptr, n, s);
+    case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+struct ChunkEv { int dev; cudaEvent_t e0, e1; };
+
+int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* status, size_t n, int ndev) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  tl_kernel_ms = 0.f;
+  OpDesc d = describe(op);
+  if (d.op < 0) return fail(FQ_ERR_ARG, "unknown operation %d", op);
+  if (n == 0) return FQ_OK;
+  if (!a || !out || (d.b_bytes && !b) || (d.status && !status)) return fail(FQ_ERR_ARG, "null buffer");
+  int count = device_count();
+  if (count < 0) return count;
+  if (ndev < 1 || g_dev_base + ndev > count) return fail(FQ_ERR_ARG, "ndev=%d with device base %d but %d device(s) visible", ndev, g_dev_base, count);
+
+  size_t per = (n + ndev - 1) / ndev;
+  std::vector<ChunkEv> evs;
+  size_t max_chunks = (per + d.chunk_rows - 1) / d.chunk_rows;
+  int rc = FQ_OK;
+  for (size_t c = 0; c < max_chunks && rc == FQ_OK; c++) {
+    for (int i = 0; i < ndev && rc == FQ_OK; i++) {
+      size_t lo = (size_t)i * per, hi = lo + per < n ? lo + per : n;
+      size_t r0 = lo + c * d.chunk_rows;
+      if (lo >= n || r0 >= hi) continue;
+      size_t rows = hi - r0 < d.chunk_rows ? hi - r0 : d.chunk_rows;
+      int dev = g_dev_base + i;
+      if ((rc = ctx_init(dev)) != FQ_OK) break;
+      DevCtx& cx = g_ctx[dev];
+      int si = (int)(c % kStreams);
+      Slot& s = cx.slot[si];
+      cudaStream_t st = cx.st[si];
+      if ((rc = slot_reserve(s, 0, d.chunk_rows * d.a_bytes)) != FQ_OK) break;
+      if (d.b_bytes && (rc = slot_reserve(s, 1, d.chunk_rows * d.b_bytes)) != FQ_OK) break;
+      if ((rc = slot_reserve(s, 2, d.chunk_rows * d.out_bytes)) != FQ_OK) break;
+      if (d.status && (rc = slot_reserve(s, 3, d.chunk_rows)) != FQ_OK) break;
+      CU(cudaMemcpyAsync(s.buf[0], a + r0 * d.a_bytes, rows * d.a_bytes, cudaMemcpyHostToDevice, st));
+      if (d.b_bytes) CU(cudaMemcpyAsync(s.buf[1], b + r0 * d.b_bytes, rows * d.b_bytes, cudaMemcpyHostToDevice, st));
+      ChunkEv ev; ev.dev = i;
+      CU(cudaEventCreate(&ev.e0)); CU(cudaEventCreate(&ev.e1));
+      CU(cudaEventRecord(ev.e0, st));
+      CU(launch(op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st));
+      CU(cudaEventRecord(ev.e1, st));
+      evs.push_back(ev);
+      CU(cudaMemcpyAsync(out + r0 * d.out_bytes, s.buf[2], rows * d.out_bytes, cudaMemcpyDeviceToHost, st));
+      if (d.status) CU(cudaMemcpyAsync(status + r0, s.buf[3], rows, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  // wait for every device, then collect kernel times
+  for (int i = 0; i < ndev; i++) {
+    int dev = g_dev_base + i;
+    if (!g_ctx[dev].ready) continue;
+    cudaSetDevice(dev);
+    for (int s = 0; s < kStreams; s++) {
+      cudaError_t e = cudaStreamSynchronize(g_ctx[dev].st[s]);
+      if (e != cudaSuccess && rc == FQ_OK) rc = fail(FQ_ERR_CUDA, "stream sync on device %d failed: %s", dev, cudaGetErrorString(e));
+    }
+  }
+  float per_dev[kMaxDev] = {0};
+  for (auto& ev : evs) {
+    float ms = 0.f;
+    if (rc == FQ_OK && cudaEventElapsedTime(&ms, ev.e0, ev.e1) == cudaSuccess) per_dev[ev.dev] += ms;
+    cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1);
+  }
+  for (int i = 0; i < ndev; i++) if (per_dev[i] > tl_kernel_ms) tl_kernel_ms = per_dev[i];
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fq_version(void) { return FQ_VERSION; }
+int fq_device_count(void) { return device_count(); }
+const char* fq_last_error(void) { return tl_err; }
+float fq_last_kernel_ms(void) { return tl_kernel_ms; }
+
+int fq_set_device_base(int first) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int count = device_count();
+  if (count < 0) return count;
+  if (first < 0 || first >= count) return fail(FQ_ERR_ARG, "device base %d out of range (%d device(s))", first, count);
+  g_dev_base = first;
+  return FQ_OK;
+}
+
+int fq_fp2_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_MUL, a, b, out, nullptr, n, ndev); }
+int fq_fp2_sqr(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SQR, a, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_inv(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_INV, a, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_add(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_ADD, a, b, out, nullptr, n, ndev); }
+int fq_fp2_sub(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SUB, a, b, out, nullptr, n, ndev); }
+int fq_fp2_neg(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_NEG, a, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_conj(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_CONJ, a, nullptr, out, nullptr, n, ndev); }
+int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE, enc, nullptr, xy, status, n, ndev); }
+int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev) { return run_host(FQ_DEVOP_ENCODE, xy, nullptr, enc, nullptr, n, ndev); }
+int fq_dh(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH, k, enc_pt, enc_out, status, n, ndev); }
+int fq_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_AFFINE, k, xy, xy_out, status, n, ndev); }
+int fq_dh_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_BASE, k, nullptr, enc_out, status, n, ndev); }
+int fq_mul_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_BASE, k, nullptr, enc_out, nullptr, n, ndev); }
+
+int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_X25519, k, u, out, nullptr, n, ndev); }
+
+int fq_host_alloc(void** p, size_t bytes) {
+  if (!p) return fail(FQ_ERR_ARG, "null pointer");
+  int count = device_count();
+  if (count < 0) return count;
+  CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+  return FQ_OK;
+}
+int fq_host_free(void* p) { if (p) CU(cudaFreeHost(p)); return FQ_OK; }
+
+static int dev_enter(int dev) {
+  int count = device_count();
+  if (count < 0) return count;
+  if (dev < 0 || dev >= count) return fail(FQ_ERR_ARG, "device %d out of range (%d device(s))", dev, count);
+  return ctx_init(dev);
+}
+int fq_dev_alloc(int dev, void** p, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  if (!p) return fail(FQ_ERR_ARG, "null pointer");
+  CU(cudaMalloc(p, bytes ? bytes : 1));
+  return FQ_OK;
+}
+int fq_dev_free(int dev, void* p) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  if (p) CU(cudaFree(p));
+  return FQ_OK;
+}
+int fq_dev_upload(int dev, void* dst, const void* src, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return FQ_OK;
+}
+int fq_dev_download(int dev, void* dst, const void* src, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return FQ_OK;
+}
+int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* status, size_t n, int iters, float* ms) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  if (describe(op).op < 0 || iters < 1) return fail(FQ_ERR_ARG, "bad op/iters");
+  cudaStream_t st = g_ctx[dev].st[0];
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; i++) CU(launch(op, a, b, out, status, n, st));
+  CU(cudaEventRecord(e1, st));
+  CU(cudaEventSynchronize(e1));
+  float t = 0.f;
+  CU(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ms) *ms = t / iters;
+  return FQ_OK;
+}
+int fq_dev_flush_l2(int dev) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  DevCtx& c = g_ctx[dev];
+  if (!c.flush) CU(cudaMalloc(&c.flush, kFlushBytes));
+  CU(cudaMemsetAsync(c.flush, 0, kFlushBytes, c.st[0]));
+  CU(cudaStreamSynchronize(c.st[0]));
+  return FQ_OK;
+}
+
+int fq_imad_peak(int dev, double* wide_per_s, double* imad32_per_s) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  int blocks = prop.multiProcessorCount * 4, trips = 8192;
+  void* scratch = nullptr;
+  CU(cudaMalloc(&scratch, (size_t)blocks * 256 * 4));
+  cudaStream_t st = g_ctx[dev].st[0];
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double res[2] = {0, 0};
+  for (int v = 0; v < 2; v++) {
+    CU(fqk_imad_peak(v, scratch, blocks, trips / 8, st));     // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+      CU(cudaEventRecord(e0, st));
+      CU(fqk_imad_peak(v, scratch, blocks, trips, st));
+      CU(cudaEventRecord(e1, st));
+      CU(cudaEventSynchronize(e1));
+      float t; CU(cudaEventElapsedTime(&t, e0, e1));
+      if (t < best) best = t;
+    }
+    res[v] = (double)blocks * 256.0 * trips * 128.0 / (best * 1e-3);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU(cudaFree(scratch));
+  if (wide_per_s) *wide_per_s = res[0];
+  if (imad32_per_s) *imad32_per_s = res[1];
+  return FQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// kernels.cu -- CUDA kernels for sm_100a.  One thread = one row everywhere; rows are read and written with 128-bit
+// vector accesses (a warp touches 1 KiB contiguous per operand).  The arithmetic lives in rows.cuh and below.
+#include "kernels.h"
+#include "rows.cuh"
+
+#define FQ_DH_THREADS 128
+#define FQ_DH_SMEM (56 * 16 * FQ_DH_THREADS)       // 7 table entries x 8 quads x 16 B per thread
+
+__constant__ u32 c_base_tabs[512];                  // table_windowed(G) | table_windowed([392]G)
+
+__device__ __forceinline__ void ld8(const void* base, size_t row, u32* w) {
+  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * row;
+  uint4 a = p[0], b = p[1];
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void st8(void* base, size_t row, const u32* w) {
+  uint4* p = reinterpret_cast<uint4*>(base) + 2 * row;
+  p[0] = make_uint4(w[0], w[1], w[2], w[3]); p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+template <int OP> __global__ void __launch_bounds__(256) k_fp2_op(const void* a, const void* b, void* out, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wa[8], wb[8], wo[8];
+  ld8(a, row, wa);
+  if (OP == FQ_OP_MUL || OP == FQ_OP_ADD || OP == FQ_OP_SUB) ld8(b, row, wb);
+  row_fp2_op<OP>(wa, wb, wo);
+  st8(out, row, wo);
+}
+
+__global__ void __launch_bounds__(256) k_decode(const void* enc, void* xy, unsigned char* status, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 we[8], wo[16];
+  ld8(enc, row, we);
+  status[row] = (unsigned char)row_decode(we, wo);
+  st8(xy, 2 * row, wo); st8(xy, 2 * row + 1, wo + 8);
+}
+
+__global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wi[16], wo[8];
+  ld8(xy, 2 * row, wi); ld8(xy, 2 * row + 1, wi + 8);
+  row_encode(wi, wo);
+  st8(enc, row, wo);
+}
+
+// variable-base DH.  AFFINE = false: fq_dh (32 B encoded point in, 32 B out); true: fq_dh_affine (64 B in, 64 B out)
+template <bool AFFINE> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
+k_dh(const void* k, const void* pt, void* out, unsigned char* status, size_t n) {
+  extern __shared__ uint4 smem[];
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  TabView T; T.base = smem + threadIdx.x; T.stride = blockDim.x;
+  u32 wk[8];
+  ld8(k, row, wk);
+  if (AFFINE) {
+    u32 wi[16], wo[16];
+    ld8(pt, 2 * row, wi); ld8(pt, 2 * row + 1, wi + 8);
+    status[row] = (unsigned char)row_dh_affine(wk, wi, wo, T);
+    st8(out, 2 * row, wo); st8(out, 2 * row + 1, wo + 8);
+  } else {
+    u32 we[8], wo[8];
+    ld8(pt, row, we);
+    status[row] = (unsigned char)row_dh(wk, we, wo, T);
+    st8(out, row, wo);
+  }
+}
+
+// fixed base: [k]G (DH = false) or [k][392]G with neutral rejection (DH = true); table in the constant bank
+template <bool DH> __global__ void __launch_bounds__(256)
+k_fixed_base(const void* k, void* out, unsigned char* status, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wk[8], wo[8];
+  ld8(k, row, wk);
+  u32 st = row_fixed_base<DH>(wk, c_base_tabs + (DH ? 256 : 0), wo);
+  if (status) status[row] = (unsigned char)st;
+  st8(out, row, wo);
+}
+
+__global__ void k_build_base_tables(u32* out, uint4* scratch) { row_build_base_tables(out, scratch); }
+
+// ---------------------------------------------------------------- integer-multiply peak (roofline denominator)
+// variant 0: IMAD.WIDE.U32 (mad.lo.cc + madc.hi), variant 1: IMAD (mad.lo.u32).  8 independent chains per thread.
+template <int V> __global__ void __launch_bounds__(256) k_imad_peak(u32* out, u32 b, int trips) {
+  u32 lo[8], hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { lo[i] = threadIdx.x + i; hi[i] = blockIdx.x + 3 * i; }
+  for (int t = 0; t < trips; t++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (V == 0) asm volatile("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.u32 %1,%2,%3,%1;" : "+r"(lo[i]), "+r"(hi[i]) : "r"(lo[(i + 4) & 7]), "r"(b));
+        else asm volatile("mad.lo.u32 %0,%0,%1,%2;" : "+r"(lo[i]) : "r"(b), "r"(hi[i]));
+      }
+    }
+  }
+  u32 s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s ^= lo[i] ^ hi[i];
+  if (s == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---------------------------------------------------------------- launch wrappers
+
+static inline unsigned grid_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+cudaError_t fqk_device_init(cudaStream_t s) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_dh<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_dh<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
+  u32* tabs = nullptr; uint4* scratch = nullptr;
+  if ((e = cudaMalloc(&tabs, 512 * sizeof(u32))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&scratch, 56 * sizeof(uint4))) != cudaSuccess) { cudaFree(tabs); return e; }
+  k_build_base_tables<<<1, 1, 0, s>>>(tabs, scratch);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_base_tabs, tabs, 512 * sizeof(u32), 0, cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(tabs); cudaFree(scratch);
+  return e;
+}
+
+cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  unsigned g = grid_for(n, 256);
+  switch (op) {
+    case FQK_MUL: k_fp2_op<FQ_OP_MUL><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQK_SQR: k_fp2_op<FQ_OP_SQR><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQK_INV: k_fp2_op<FQ_OP_INV><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQK_ADD: k_fp2_op<FQ_OP_ADD><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQK_SUB: k_fp2_op<FQ_OP_SUB><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQK_NEG: k_fp2_op<FQ_OP_NEG><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQK_CONJ: k_fp2_op<FQ_OP_CONJ><<<g, 256, 0, s>>>(a, b, out, n); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t fqk_decode(const void* enc, void* xy, void* status, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_decode<<<grid_for(n, 256), 256, 0, s>>>(enc, xy, (unsigned char*)status, n);
+  return cudaGetLastError();
+}
+cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_encode<<<grid_for(n, 256), 256, 0, s>>>(xy, enc, n);
+  return cudaGetLastError();
+}
+cudaError_t fqk_dh(int affine, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  unsigned g = grid_for(n, FQ_DH_THREADS);
+  if (affine) k_dh<true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, (unsigned char*)status, n);
+  else k_dh<false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, (unsigned char*)status, n);
+  return cudaGetLastError();
+}
+cudaError_t fqk_fixed_base(int dh, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  unsigned g = grid_for(n, 256);
+  if (dh) k_fixed_base<true><<<g, 256, 0, s>>>(k, out, (unsigned char*)status, n);
+  else k_fixed_base<false><<<g, 256, 0, s>>>(k, out, (unsigned char*)status, n);
+  return cudaGetLastError();
+}
+cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s) {
+  if (variant == 0) k_imad_peak<0><<<blocks, 256, 0, s>>>((u32*)scratch, 0x9e3779b9u, trips);
+  else k_imad_peak<1><<<blocks, 256, 0, s>>>((u32*)scratch, 0x9e3779b9u, trips);
+  return cudaGetLastError();
+}

@@ -1,0 +1,201 @@
+// x25519.cuh -- batched X25519 (RFC 7748), the comparison curve of the reference (impl/curve25519.py:17-91 with
+// GFp25519 of impl/fields.py:240-362).  GF(2^255-19) elements are 8 x 32-bit limbs kept "loose" (any value < 2^256,
+// congruent mod p); 2^256 = 38 (mod p).  Multiplication: 64 IMAD.WIDE in even/odd 64-bit lattices, then 8 more for
+// the 38 * hi fold.  One thread = one ladder (255 steps, cswap by masks, curve25519.py:51-76).
+#pragma once
+#include "arith.cuh"
+
+struct f25 { u32 v[8]; };
+
+FQ_FN f25 f25_small(u32 x) { f25 r; r.v[0] = x; FQ_UNROLL for (int i = 1; i < 8; i++) r.v[i] = 0; return r; }
+
+// r + 38*c for a carry/borrow correction c in {0,1}; cannot overflow twice
+FQ_FN f25 f25_fix_carry(f25 r, u32 c) {
+  u32 k = 38u * c;
+  r.v[0] = add_cc(r.v[0], k);
+  FQ_UNROLL
+  for (int i = 1; i < 8; i++) r.v[i] = addc_cc(r.v[i], 0);
+  u32 c2 = addc(0, 0);
+  r.v[0] += 38u * c2;               // after a wrap the value is < 38, no further carry
+  return r;
+}
+// fields.py:267-270
+FQ_FN f25 f25_add(const f25& a, const f25& b) {
+  f25 r;
+  r.v[0] = add_cc(a.v[0], b.v[0]);
+  FQ_UNROLL
+  for (int i = 1; i < 8; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+  return f25_fix_carry(r, addc(0, 0));
+}
+// fields.py:273-276.  a - b wraps to a - b + 2^256 = a - b + 38 (mod p): take the 38 back.
+FQ_FN f25 f25_sub(const f25& a, const f25& b) {
+  f25 r;
+  r.v[0] = sub_cc(a.v[0], b.v[0]);
+  FQ_UNROLL
+  for (int i = 1; i < 8; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+  u32 bw = 0u - subc(0, 0);         // 1 if borrow
+  u32 k = 38u * bw;
+  r.v[0] = sub_cc(r.v[0], k);
+  FQ_UNROLL
+  for (int i = 1; i < 8; i++) r.v[i] = subc_cc(r.v[i], 0);
+  u32 bw2 = 0u - subc(0, 0);
+  r.v[0] -= 38u * bw2;              // after a second wrap the value is >= 2^256 - 38, no further borrow
+  return r;
+}
+// fields.py:259-264: m all ones swaps
+FQ_FN void f25_cswap(u32 m, f25& x, f25& y) {
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) { u32 t = m & (x.v[i] ^ y.v[i]); x.v[i] ^= t; y.v[i] ^= t; }
+}
+
+// 9-limb value t (t[8] small) -> loose 8-limb: t[0..7] + 38 * t[8]
+FQ_FN f25 f25_fold9(const u32* t) {
+  f25 r;
+  u32 lo, hi;
+  mul_wide(lo, hi, t[8], 38u);
+  r.v[0] = add_cc(t[0], lo); r.v[1] = addc_cc(t[1], hi);
+  FQ_UNROLL
+  for (int i = 2; i < 8; i++) r.v[i] = addc_cc(t[i], 0);
+  return f25_fix_carry(r, addc(0, 0));
+}
+
+// fields.py:279-282
+FQ_FN f25 f25_mul(const f25& a, const f25& b) {
+  // E[k] holds limb k of the even lattice, O[k] limb k+1 of the odd lattice
+  u32 E[16], O[16];
+  FQ_UNROLL
+  for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) {
+    // products a_j * b_i at limb position i + j
+    FQ_UNROLL
+    for (int par = 0; par < 2; par++) {
+      // par = parity of j handled by this chain
+      const bool even_pos = ((i + par) & 1) == 0;
+      u32* A = even_pos ? E : O;
+      const int base = even_pos ? (i + par) : (i + par - 1);
+      FQ_UNROLL
+      for (int jj = 0; jj < 4; jj++) {
+        const int j = 2 * jj + par, k = base + 2 * jj;
+        if (jj == 0) { A[k] = mad_lo_cc(a.v[j], b.v[i], A[k]); A[k + 1] = madc_hi_cc(a.v[j], b.v[i], A[k + 1]); }
+        else { A[k] = madc_lo_cc(a.v[j], b.v[i], A[k]); A[k + 1] = madc_hi_cc(a.v[j], b.v[i], A[k + 1]); }
+      }
+      if (base + 8 < 16) A[base + 8] = addc(A[base + 8], 0);
+    }
+  }
+  // merge: m = E + (O << 32)
+  u32 m[16];
+  m[0] = E[0];
+  m[1] = add_cc(E[1], O[0]);
+  FQ_UNROLL
+  for (int k = 2; k < 15; k++) m[k] = addc_cc(E[k], O[k - 1]);
+  m[15] = addc(E[15], O[14]);
+  // t = m[0..7] + 38 * m[8..15]  (9 limbs)
+  u32 t[9], P[9];
+  FQ_UNROLL
+  for (int k = 0; k < 8; k++) t[k] = m[k];
+  t[0] = mad_lo_cc(m[8], 38u, t[0]); t[1] = madc_hi_cc(m[8], 38u, t[1]);
+  t[2] = madc_lo_cc(m[10], 38u, t[2]); t[3] = madc_hi_cc(m[10], 38u, t[3]);
+  t[4] = madc_lo_cc(m[12], 38u, t[4]); t[5] = madc_hi_cc(m[12], 38u, t[5]);
+  t[6] = madc_lo_cc(m[14], 38u, t[6]); t[7] = madc_hi_cc(m[14], 38u, t[7]);
+  t[8] = addc(0, 0);
+  mul_wide(P[1], P[2], m[9], 38u); mul_wide(P[3], P[4], m[11], 38u);
+  mul_wide(P[5], P[6], m[13], 38u); mul_wide(P[7], P[8], m[15], 38u);
+  t[1] = add_cc(t[1], P[1]);
+  FQ_UNROLL
+  for (int k = 2; k < 8; k++) t[k] = addc_cc(t[k], P[k]);
+  t[8] = addc(t[8], P[8]);
+  return f25_fold9(t);
+}
+FQ_FN f25 f25_sqr(const f25& a) { return f25_mul(a, a); }   // fields.py:285-288
+
+// a * 121665 (curve25519.py:76, a24)
+FQ_FN f25 f25_mul_a24(const f25& a) {
+  u32 t[9], P[9];
+  const u32 c = 121665u;
+  mul_wide(t[0], t[1], a.v[0], c); mul_wide(t[2], t[3], a.v[2], c); mul_wide(t[4], t[5], a.v[4], c); mul_wide(t[6], t[7], a.v[6], c);
+  mul_wide(P[1], P[2], a.v[1], c); mul_wide(P[3], P[4], a.v[3], c); mul_wide(P[5], P[6], a.v[5], c); mul_wide(P[7], P[8], a.v[7], c);
+  t[1] = add_cc(t[1], P[1]);
+  FQ_UNROLL
+  for (int k = 2; k < 8; k++) t[k] = addc_cc(t[k], P[k]);
+  t[8] = addc(0, P[8]);
+  return f25_fold9(t);
+}
+
+FQ_FN f25 f25_nsqr(f25 x, int n) {
+  FQ_NOUNROLL
+  for (int i = 0; i < n; i++) x = f25_sqr(x);
+  return x;
+}
+// fields.py:293-362: z^(p-2) = z^(2^255 - 21), same chain shape (254 S + 11 M)
+FQ_FN f25 f25_inv(const f25& z) {
+  f25 z2 = f25_sqr(z);
+  f25 z9 = f25_mul(f25_nsqr(z2, 2), z);
+  f25 z11 = f25_mul(z9, z2);
+  f25 z2_5_0 = f25_mul(f25_sqr(z11), z9);
+  f25 z2_10_0 = f25_mul(f25_nsqr(z2_5_0, 5), z2_5_0);
+  f25 z2_20_0 = f25_mul(f25_nsqr(z2_10_0, 10), z2_10_0);
+  f25 z2_40_0 = f25_mul(f25_nsqr(z2_20_0, 20), z2_20_0);
+  f25 z2_50_0 = f25_mul(f25_nsqr(z2_40_0, 10), z2_10_0);
+  f25 z2_100_0 = f25_mul(f25_nsqr(z2_50_0, 50), z2_50_0);
+  f25 z2_200_0 = f25_mul(f25_nsqr(z2_100_0, 100), z2_100_0);
+  f25 z2_250_0 = f25_mul(f25_nsqr(z2_200_0, 50), z2_50_0);
+  return f25_mul(f25_nsqr(z2_250_0, 5), z11);
+}
+
+// loose -> canonical representative in [0, p)
+FQ_FN f25 f25_canon(f25 r) {
+  // fold bit 255: r = (r mod 2^255) + 19 * (r >> 255)  < 2^255 + 19
+  u32 top = r.v[7] >> 31;
+  r.v[7] &= 0x7fffffffu;
+  r.v[0] = add_cc(r.v[0], 19u * top);
+  FQ_UNROLL
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(r.v[i], 0);
+  r.v[7] = addc(r.v[7], 0);
+  // r >= p  <=>  r + 19 >= 2^255
+  f25 s;
+  s.v[0] = add_cc(r.v[0], 19u);
+  FQ_UNROLL
+  for (int i = 1; i < 7; i++) s.v[i] = addc_cc(r.v[i], 0);
+  s.v[7] = addc(r.v[7], 0);
+  u32 ge = 0u - (s.v[7] >> 31);     // all ones if r >= p; then r - p = (r + 19) mod 2^255
+  s.v[7] &= 0x7fffffffu;
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) r.v[i] = (s.v[i] & ge) | (r.v[i] & ~ge);
+  return r;
+}
+
+// curve25519.py:88-91: k, u, out = 8 little-endian words each
+FQ_FN void row_x25519(const u32* kw, const u32* uw, u32* out) {
+  u32 k[8];
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) k[i] = kw[i];
+  k[0] &= 0xfffffff8u; k[7] = (k[7] & 0x7fffffffu) | 0x40000000u;           // curve25519.py:20-25
+  f25 x1;
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) x1.v[i] = uw[i];
+  x1.v[7] &= 0x7fffffffu;                                                    // curve25519.py:27-33
+  f25 x2 = f25_small(1), z2 = f25_small(0), x3 = x1, z3 = f25_small(1);
+  u32 swap = 0;
+  FQ_NOUNROLL
+  for (int t = 254; t >= 0; t--) {                                           // curve25519.py:51-76
+    u32 kt = (k[t >> 5] >> (t & 31)) & 1;
+    u32 m = 0u - (swap ^ kt);
+    f25_cswap(m, x2, x3); f25_cswap(m, z2, z3);
+    swap = kt;
+    f25 A = f25_add(x2, z2), B = f25_sub(x2, z2);
+    f25 AA = f25_sqr(A), BB = f25_sqr(B);
+    f25 E = f25_sub(AA, BB);
+    f25 C = f25_add(x3, z3), D = f25_sub(x3, z3);
+    f25 DA = f25_mul(D, A), CB = f25_mul(C, B);
+    x3 = f25_sqr(f25_add(DA, CB));
+    z3 = f25_mul(x1, f25_sqr(f25_sub(DA, CB)));
+    x2 = f25_mul(AA, BB);
+    z2 = f25_mul(E, f25_add(AA, f25_mul_a24(E)));
+  }
+  u32 m = 0u - swap;
+  f25_cswap(m, x2, x3); f25_cswap(m, z2, z3);                                 // curve25519.py:78-79
+  f25 r = f25_canon(f25_mul(x2, f25_inv(z2)));                                // curve25519.py:80, 35-39
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) out[i] = r.v[i];
+}

@@ -1,0 +1,121 @@
+"""Batched Curve4Q -- the counterpart of the reference's impl/curve4q.py entry points.
+
+    reference (one element, Python ints)            here (N rows, numpy uint8)
+    encode(X, Y) -> bytearray(32)      :41-46       encode(XY[N,64]) -> B[N,32]
+    decode(B) -> (x, y) or raises      :49-96       decode(B[N,32]) -> (XY[N,64], status[N])
+    DH_windowed(m, P) -> affine Q      :464-465     DH_windowed(k[N,32], XY[N,64]) -> (XY[N,64], status[N])
+    encode(DH_windowed(m, decode(B)))               DH(k[N,32], B[N,32]) -> (B[N,32], status[N])
+    DH_windowed(m, G, table=T392)      :743-762     DH_base(k[N,32]) -> (B[N,32], status[N])
+    MUL_windowed(m, G, table=T) -> [m]G :582-584    MUL_base(k[N,32]) -> B[N,32]
+
+Scalars are 32-byte little-endian unsigned rows (no clamping).  Exceptions of the reference become per-row status codes;
+failed rows are zero-filled.  `strict=True` raises the reference's message for the first failing row instead.
+decode() does not modify its argument (the reference clears bits in place, curve4q.py:56).
+"""
+import numpy as np
+
+from . import _lib
+
+ST_OK, ST_RESERVED_BIT, ST_NONCANONICAL, ST_QUIRK_T0, ST_NOT_ON_CURVE, ST_NEUTRAL = range(6)
+
+# messages of the reference's exceptions (curve4q.py:53, :62, :77 (AttributeError), :94/:448, :460)
+STATUS_MESSAGES = {
+    ST_RESERVED_BIT: "Malformed point: reserved bit is not zero",
+    ST_NONCANONICAL: "Malformed point: reserved bit is not zero",
+    ST_QUIRK_T0: "type object 'GFp' has no attribute 'two'",
+    ST_NOT_ON_CURVE: "Point not on curve",
+    ST_NEUTRAL: "DH computation resulted in neutral point",
+}
+
+# curve4q.py:9-20
+d = (0xe40000000000000142, 0x5e472f846657e0fcb3821488f1fc0c8d)
+N = 0x29cbc14e5e0a72f05397829cbc14e5dfbd004dfe0f79992fb2540ec7768ce7
+Gx = (0x1A3472237C2FB305286592AD7B3833AA, 0x1E1F553F2878AA9C96869FB360AC77F6)
+Gy = (0x0E3FEE9BA120785AB924A2462BCBB287, 0x6E1C4AF8630E024249A7C344844C8B5C)
+
+
+def _raise_first(status):
+    bad = np.flatnonzero(status)
+    if bad.size:
+        st = int(status[bad[0]])
+        exc = AttributeError if st == ST_QUIRK_T0 else Exception
+        raise exc("%s (row %d)" % (STATUS_MESSAGES[st], int(bad[0])))
+
+
+def encode(XY, ndev=1):
+    XY = _lib.rows(XY, 64, "XY")
+    out = np.empty((XY.shape[0], 32), np.uint8)
+    _lib.check(_lib.lib().fq_encode(_lib.ptr(XY), _lib.ptr(out), XY.shape[0], ndev))
+    return out
+
+
+def decode(B, ndev=1, strict=False):
+    B = _lib.rows(B, 32, "B")
+    n = B.shape[0]
+    XY = np.empty((n, 64), np.uint8)
+    status = np.empty(n, np.uint8)
+    _lib.check(_lib.lib().fq_decode(_lib.ptr(B), _lib.ptr(XY), _lib.ptr(status), n, ndev))
+    if strict:
+        _raise_first(status)
+    return XY, status
+
+
+def DH(k, B, ndev=1, strict=False):
+    k = _lib.rows(k, 32, "k")
+    B = _lib.rows(B, 32, "B")
+    if k.shape[0] != B.shape[0]:
+        raise ValueError("k and B must have the same number of rows")
+    n = k.shape[0]
+    out = np.empty((n, 32), np.uint8)
+    status = np.empty(n, np.uint8)
+    _lib.check(_lib.lib().fq_dh(_lib.ptr(k), _lib.ptr(B), _lib.ptr(out), _lib.ptr(status), n, ndev))
+    if strict:
+        _raise_first(status)
+    return out, status
+
+
+def DH_windowed(k, XY, ndev=1, strict=False):
+    k = _lib.rows(k, 32, "k")
+    XY = _lib.rows(XY, 64, "XY")
+    if k.shape[0] != XY.shape[0]:
+        raise ValueError("k and XY must have the same number of rows")
+    n = k.shape[0]
+    out = np.empty((n, 64), np.uint8)
+    status = np.empty(n, np.uint8)
+    _lib.check(_lib.lib().fq_dh_affine(_lib.ptr(k), _lib.ptr(XY), _lib.ptr(out), _lib.ptr(status), n, ndev))
+    if strict:
+        _raise_first(status)
+    return out, status
+
+
+def DH_base(k, ndev=1, strict=False):
+    k = _lib.rows(k, 32, "k")
+    n = k.shape[0]
+    out = np.empty((n, 32), np.uint8)
+    status = np.empty(n, np.uint8)
+    _lib.check(_lib.lib().fq_dh_base(_lib.ptr(k), _lib.ptr(out), _lib.ptr(status), n, ndev))
+    if strict:
+        _raise_first(status)
+    return out, status
+
+
+def MUL_base(k, ndev=1):
+    k = _lib.rows(k, 32, "k")
+    out = np.empty((k.shape[0], 32), np.uint8)
+    _lib.check(_lib.lib().fq_mul_base(_lib.ptr(k), _lib.ptr(out), k.shape[0], ndev))
+    return out
+
+
+def pack_affine(points):
+    """[((x0, x1), (y0, y1)), ...] Python ints -> (N, 64) rows."""
+    out = np.empty((len(points), 64), np.uint8)
+    for i, (x, y) in enumerate(points):
+        out[i] = np.frombuffer(b"".join(int(v).to_bytes(16, "little") for v in (x[0], x[1], y[0], y[1])), np.uint8)
+    return out
+
+
+def pack_scalars(ms):
+    out = np.empty((len(ms), 32), np.uint8)
+    for i, m in enumerate(ms):
+        out[i] = np.frombuffer((int(m) % (1 << 256)).to_bytes(32, "little"), np.uint8)
+    return out

@@ -1,0 +1,102 @@
+"""Device selection, pinned host arrays and device-resident buffers (measurement helpers; bench.py uses these)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def device_count():
+    n = _lib.lib().fq_device_count()
+    if n < 0:
+        _lib.check(n)
+    return n
+
+
+def set_device(first):
+    """GPUs used by the host entry points become first .. first+ndev-1 (one process per GPU passes LOCAL_RANK)."""
+    _lib.check(_lib.lib().fq_set_device_base(int(first)))
+
+
+def last_kernel_ms():
+    return float(_lib.lib().fq_last_kernel_ms())
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.ptr = ctypes.c_void_p()
+        _lib.check(_lib.lib().fq_host_alloc(ctypes.byref(self.ptr), nbytes))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().fq_host_free(self.ptr)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class _PinnedArray(np.ndarray):
+    _fq_owner = None
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array backed by page-locked host memory (cudaHostAlloc): host entry points then copy without staging."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    owner = _Pinned(max(nbytes, 1))
+    buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(owner.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape).view(_PinnedArray)
+    arr._fq_owner = owner
+    return arr
+
+
+class DeviceBuffer:
+    """A raw device allocation on one GPU."""
+
+    def __init__(self, dev, nbytes):
+        self.dev, self.nbytes = int(dev), int(nbytes)
+        self.ptr = ctypes.c_void_p()
+        _lib.check(_lib.lib().fq_dev_alloc(self.dev, ctypes.byref(self.ptr), self.nbytes))
+
+    @classmethod
+    def from_host(cls, dev, arr):
+        arr = np.ascontiguousarray(arr)
+        b = cls(dev, arr.nbytes)
+        _lib.check(_lib.lib().fq_dev_upload(b.dev, b.ptr, _lib.ptr(arr), arr.nbytes))
+        return b
+
+    def to_host(self, shape, dtype=np.uint8):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        _lib.check(_lib.lib().fq_dev_download(self.dev, _lib.ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            _lib.check(_lib.lib().fq_dev_free(self.dev, self.ptr))
+            self.ptr = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def dev_run(op, dev, a, b, out, status, n, iters=1):
+    """Launches the kernel of `op` (a key of _lib.DEVOP) on device buffers; returns average milliseconds per launch."""
+    ms = ctypes.c_float()
+    g = lambda x: x.ptr if x is not None else None  # noqa: E731
+    _lib.check(_lib.lib().fq_dev_run(_lib.DEVOP[op], int(dev), g(a), g(b), g(out), g(status), int(n), int(iters), ctypes.byref(ms)))
+    return float(ms.value)
+
+
+def flush_l2(dev):
+    _lib.check(_lib.lib().fq_dev_flush_l2(int(dev)))
+
+
+def imad_peak(dev=0):
+    """(IMAD.WIDE.U32 per second, 32-bit IMAD per second) measured on the device: the integer-multiply roofline."""
+    w, s = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.lib().fq_imad_peak(int(dev), ctypes.byref(w), ctypes.byref(s)))
+    return float(w.value), float(s.value)

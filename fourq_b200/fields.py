@@ -1,0 +1,76 @@
+"""Batched GF((2^127-1)^2) arithmetic -- the counterpart of the reference's impl/fields.py class GFp2.
+
+An element is a 32-byte row LE128(re) | LE128(im); arrays are (N, 32) uint8.  Like the reference's functions on Python
+ints (fields.py:157-199) any 128-bit value per half is accepted and results are canonical (< p)."""
+import numpy as np
+
+from . import _lib
+
+p1271 = (1 << 127) - 1      # fields.py:5
+
+
+def _unary(fn_name, a, ndev):
+    a = _lib.rows(a, 32, "a")
+    out = np.empty_like(a)
+    _lib.check(getattr(_lib.lib(), fn_name)(_lib.ptr(a), _lib.ptr(out), a.shape[0], ndev))
+    return out
+
+
+def _binary(fn_name, a, b, ndev):
+    a = _lib.rows(a, 32, "a")
+    b = _lib.rows(b, 32, "b")
+    if a.shape != b.shape:
+        raise ValueError("operands must have the same shape")
+    out = np.empty_like(a)
+    _lib.check(getattr(_lib.lib(), fn_name)(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], ndev))
+    return out
+
+
+class GFp2:
+    """Static methods named after fields.py GFp2.*"""
+
+    @staticmethod
+    def mul(a, b, ndev=1):       # fields.py:167-173
+        return _binary("fq_fp2_mul", a, b, ndev)
+
+    @staticmethod
+    def sqr(a, ndev=1):          # fields.py:176-181
+        return _unary("fq_fp2_sqr", a, ndev)
+
+    @staticmethod
+    def inv(a, ndev=1):          # fields.py:194-199
+        return _unary("fq_fp2_inv", a, ndev)
+
+    @staticmethod
+    def add(a, b, ndev=1):       # fields.py:157-159
+        return _binary("fq_fp2_add", a, b, ndev)
+
+    @staticmethod
+    def sub(a, b, ndev=1):       # fields.py:162-164
+        return _binary("fq_fp2_sub", a, b, ndev)
+
+    @staticmethod
+    def neg(a, ndev=1):          # fields.py:184-186
+        return _unary("fq_fp2_neg", a, ndev)
+
+    @staticmethod
+    def conj(a, ndev=1):         # fields.py:189-191
+        return _unary("fq_fp2_conj", a, ndev)
+
+    @staticmethod
+    def select(c, x, y):         # fields.py:237-238; c is a (N,) 0/1 array.  Pure data movement, done by numpy.
+        c = np.asarray(c).astype(bool).reshape(-1, 1)
+        return np.where(c, _lib.rows(x, 32, "x"), _lib.rows(y, 32, "y"))
+
+
+def pack(pairs):
+    """[(re, im), ...] Python ints -> (N, 32) uint8 rows (fields.py:125-126 packing of each half)."""
+    out = np.empty((len(pairs), 32), np.uint8)
+    for i, (re, im) in enumerate(pairs):
+        out[i] = np.frombuffer(int(re).to_bytes(16, "little") + int(im).to_bytes(16, "little"), np.uint8)
+    return out
+
+
+def unpack(rows):
+    rows = _lib.rows(rows, 32)
+    return [(int.from_bytes(bytes(r[:16]), "little"), int.from_bytes(bytes(r[16:]), "little")) for r in rows]

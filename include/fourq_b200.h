@@ -1,0 +1,124 @@
+/* fourq_b200.h -- C ABI of the B200-native batched Curve4Q engine (libfourq_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of bifurcation/fourq.  The reference has no FFI: its boundary is the
+ * set of Python functions in impl/curve4q.py, impl/fields.py and impl/curve25519.py.  Every entry point below names the
+ * reference function it replaces; fourq_b200/ (Python, ctypes) mirrors those names in batched form.
+ *
+ * Conventions
+ *   - all buffers are caller-owned, C-contiguous, little-endian byte rows:
+ *       GF(p^2) element   32 B = LE128(re) | LE128(im)          (fields.py:125-132 packing, two halves)
+ *       affine point      64 B = x | y                          (two GF(p^2) elements)
+ *       encoded point     32 B                                   (curve4q.py:41-46)
+ *       scalar            32 B  little-endian unsigned, no clamping (curve4q.py:558-559 limb order)
+ *   - host entry points take HOST pointers (pageable or pinned) and run on `ndev` GPUs, rows split in contiguous
+ *     slices (device i gets rows [i*ceil(n/ndev), ...)); there is no collective and no CPU fallback: with no CUDA
+ *     device every call returns FQ_ERR_NO_DEVICE.
+ *   - return value: 0 (FQ_OK) or a negative FQ_ERR_*; fq_last_error() gives the text (thread-local).
+ *   - per-row outcome in status[n] (uint8): see FQ_ST_*.  Rows that fail are zero-filled in the output.
+ *   - thread-safe: calls are serialised by an internal mutex; per-device contexts are created lazily.
+ */
+#ifndef FOURQ_B200_H
+#define FOURQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQ_VERSION 100
+
+#if defined(__GNUC__)
+#define FQ_API __attribute__((visibility("default")))
+#else
+#define FQ_API
+#endif
+
+#define FQ_OK 0
+#define FQ_ERR_NO_DEVICE (-1)   /* no CUDA device / driver: the engine has no CPU path */
+#define FQ_ERR_CUDA (-2)        /* a CUDA call failed; see fq_last_error() */
+#define FQ_ERR_ARG (-3)         /* null pointer, ndev out of range, ... */
+
+/* per-row status codes */
+#define FQ_ST_OK 0
+#define FQ_ST_RESERVED_BIT 1    /* curve4q.py:52-53  "Malformed point: reserved bit is not zero" (bit 127 of y0) */
+#define FQ_ST_NONCANONICAL 2    /* curve4q.py:61-62  y0 >= p or y1 >= p (same message in the reference) */
+#define FQ_ST_QUIRK_T0 3        /* curve4q.py:76-77  the reference raises AttributeError (GFp.two) when t == 0 */
+#define FQ_ST_NOT_ON_CURVE 4    /* curve4q.py:93-94, 447-448  "Point not on curve" */
+#define FQ_ST_NEUTRAL 5         /* curve4q.py:459-460  "DH computation resulted in neutral point" */
+
+FQ_API int fq_version(void);
+FQ_API int fq_device_count(void);                 /* >= 0, or FQ_ERR_NO_DEVICE */
+FQ_API const char* fq_last_error(void);
+/* GPUs used by the host entry points are first .. first+ndev-1 (default 0).  One process per GPU sets its LOCAL_RANK. */
+FQ_API int fq_set_device_base(int first);
+/* kernel-only milliseconds (CUDA events, max over devices of the per-device sum) of the last host call of this thread */
+FQ_API float fq_last_kernel_ms(void);
+
+/* ---- GF(p^2) field ops: fields.py GFp2.mul :167, sqr :176, inv :194, add :157, sub :162, neg :184, conj :189.
+ * Inputs may be any 128-bit values per half (the reference reduces ints mod p); outputs are canonical. */
+FQ_API int fq_fp2_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
+FQ_API int fq_fp2_sqr(const uint8_t* a, uint8_t* out, size_t n, int ndev);
+FQ_API int fq_fp2_inv(const uint8_t* a, uint8_t* out, size_t n, int ndev);
+FQ_API int fq_fp2_add(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
+FQ_API int fq_fp2_sub(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
+FQ_API int fq_fp2_neg(const uint8_t* a, uint8_t* out, size_t n, int ndev);
+FQ_API int fq_fp2_conj(const uint8_t* a, uint8_t* out, size_t n, int ndev);
+
+/* ---- point codec: curve4q.py decode :49-96 (enc (n,32) -> xy (n,64) + status), encode :41-46 (xy -> enc).
+ * Unlike the reference, decode does not modify its input. */
+FQ_API int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev);
+FQ_API int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev);
+
+/* ---- Diffie-Hellman
+ * fq_dh:        encode(DH_windowed(k, decode(enc_pt)))            curve4q.py:49, 446-465, 41
+ * fq_dh_affine: DH_windowed(k, (x, y)) on affine 64-byte points   curve4q.py:446-465
+ * fq_dh_base:   encode(DH_windowed(k, G, table=T392)) = [392 k]G  curve4q.py:743-762
+ * fq_mul_base:  encode(R1toAffine(MUL_windowed(k, G, table=table_windowed(G)))) = [k]G   curve4q.py:582-584 (no status:
+ *               MUL_windowed has no failure path; k = 0 mod N gives the encoding of the neutral point) */
+FQ_API int fq_dh(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev);
+FQ_API int fq_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev);
+FQ_API int fq_dh_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev);
+FQ_API int fq_mul_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev);
+
+/* ---- X25519 (RFC 7748): impl/curve25519.py:88-91 x25519(k, u) -> 32 bytes; k, u, out are (n,32) */
+FQ_API int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev);
+
+/* ---- pinned host memory for zero-staging transfers (optional; any host pointer is accepted above) */
+FQ_API int fq_host_alloc(void** p, size_t bytes);
+FQ_API int fq_host_free(void* p);
+
+/* ---- device-resident variants, for measurement with inputs already in HBM (bench.py `value`, ncu).
+ * op: one of FQ_DEVOP_*; pointers are device pointers on GPU `dev`; the kernel is launched `iters` times back to back on
+ * the context's stream and *ms receives the average CUDA-event time of one launch. */
+#define FQ_DEVOP_FP2_MUL 0
+#define FQ_DEVOP_FP2_SQR 1
+#define FQ_DEVOP_FP2_INV 2
+#define FQ_DEVOP_FP2_ADD 3
+#define FQ_DEVOP_FP2_SUB 4
+#define FQ_DEVOP_FP2_NEG 5
+#define FQ_DEVOP_FP2_CONJ 6
+#define FQ_DEVOP_DECODE 16     /* a = enc, out = xy, status */
+#define FQ_DEVOP_ENCODE 17     /* a = xy, out = enc */
+#define FQ_DEVOP_DH 18         /* a = k, b = enc_pt, out, status */
+#define FQ_DEVOP_DH_AFFINE 19  /* a = k, b = xy, out = xy, status */
+#define FQ_DEVOP_DH_BASE 20    /* a = k, out, status */
+#define FQ_DEVOP_MUL_BASE 21   /* a = k, out */
+#define FQ_DEVOP_X25519 22     /* a = k, b = u, out */
+FQ_API int fq_dev_alloc(int dev, void** p, size_t bytes);
+FQ_API int fq_dev_free(int dev, void* p);
+FQ_API int fq_dev_upload(int dev, void* dst, const void* src, size_t bytes);
+FQ_API int fq_dev_download(int dev, void* dst, const void* src, size_t bytes);
+FQ_API int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* status, size_t n, int iters, float* ms);
+/* writes `bytes` of zeros over a scratch buffer larger than L2 (used between timed iterations) */
+FQ_API int fq_dev_flush_l2(int dev);
+
+/* ---- integer-multiply peak of GPU `dev`, measured live: 32x32->64 multiply-adds per second as IMAD.WIDE.U32
+ * (the instruction the limb arithmetic is made of) and 32-bit IMAD per second.  The roofline denominator. */
+FQ_API int fq_imad_peak(int dev, double* wide_per_s, double* imad32_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

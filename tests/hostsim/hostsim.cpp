@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstddef>
 #include "../../fourq_b200/csrc/rows.cuh"
+#include "../../fourq_b200/csrc/x25519.cuh"
 
 namespace fqsim { thread_local u32 cc = 0; }
 
@@ -100,6 +101,14 @@ int sim_recode(const uint8_t* k, uint8_t* idx, uint8_t* neg, uint8_t* reduced) {
   memcpy(reduced, r.v, 32);
   scal S = scal_digits_init(r);
   for (int i = 0; i < 62; i++) { u32 a, b; scal_next_digit(S, a, b); idx[i] = (uint8_t)a; neg[i] = (uint8_t)(b & 1); }
+  return 0;
+}
+int sim_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wk[8], wu[8], wo[8]; memcpy(wk, k + 32 * i, 32); memcpy(wu, u + 32 * i, 32);
+    row_x25519(wk, wu, wo);
+    memcpy(out + 32 * i, wo, 32);
+  }
   return 0;
 }
 }  // extern "C"

@@ -1,0 +1,214 @@
+"""GPU parity tests (run on the B200 with -m gpu).  Everything goes through the Python facade -> ctypes -> C ABI ->
+CUDA kernels and is compared bit-for-bit with (a) the golden vectors generated from the reference's own code and
+(b) the CPU oracle on seeded random inputs; at BASELINE sizes (2^20) size-independent properties are checked."""
+import multiprocessing as mp
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import fourq_oracle as O
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def fq():
+    import fourq_b200
+    assert fourq_b200.device_count() >= 1        # raises if the CUDA library or device is missing: no silent fallback
+    return fourq_b200
+
+
+def R(lst):
+    return np.frombuffer(b"".join(lst), np.uint8).reshape(len(lst), -1).copy()
+
+
+def hexrows(a):
+    return [bytes(r).hex() for r in a]
+
+
+# ---------------------------------------------------------------- golden vectors (from the reference's code)
+
+@pytest.mark.parametrize("op", ["mul", "add", "sub"])
+def test_fp2_binary_golden(fq, golden, op):
+    rows = golden["fields"][op]
+    got = getattr(fq.GFp2, op)(R([H(r[0]) for r in rows]), R([H(r[1]) for r in rows]))
+    assert hexrows(got) == [r[2] for r in rows]
+
+
+@pytest.mark.parametrize("op", ["sqr", "neg", "conj", "inv"])
+def test_fp2_unary_golden(fq, golden, op):
+    rows = golden["fields"][op]
+    got = getattr(fq.GFp2, op)(R([H(r[0]) for r in rows]))
+    assert hexrows(got) == [r[1] for r in rows]
+
+
+def test_codec_golden(fq, golden):
+    c = golden["codec"]
+    assert hexrows(fq.encode(R([H(r[0]) for r in c["encode"]]))) == [r[1] for r in c["encode"]]
+    B = R([H(r[0]) for r in c["decode"]])
+    keep = B.copy()
+    XY, st = fq.decode(B)
+    assert (B == keep).all()                     # no in-place mutation (the reference mutates, curve4q.py:56)
+    assert [(int(s), x) for s, x in zip(st, hexrows(XY))] == [(r[1], r[2]) for r in c["decode"]]
+    assert set(int(s) for s in st) == {0, 1, 2, 3, 4}
+
+
+def test_scalar_mult_golden(fq, golden):
+    m = golden["mul"]
+    assert hexrows(fq.MUL_base(R([H(r[0]) for r in m["mul_base"]]))) == [r[1] for r in m["mul_base"]]
+    out, st = fq.DH_base(R([H(r[0]) for r in m["dh_base"]]))
+    assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[1], r[2]) for r in m["dh_base"]]
+    out, st = fq.DH(R([H(r[0]) for r in m["dh"]]), R([H(r[1]) for r in m["dh"]]))
+    assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh"]]
+    assert set(int(s) for s in st) == {0, 1, 2, 3, 4, 5}
+    out, st = fq.DH_windowed(R([H(r[0]) for r in m["dh_affine"]]), R([H(r[1]) for r in m["dh_affine"]]))
+    assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh_affine"]]
+
+
+def test_reference_mulP_chain(fq, golden):
+    """curve4q.py:549-567: 1000 chained MUL_windowed from G end at mulP, i.e. [prod c_i mod N]G == mulP."""
+    m = golden["mul"]
+    prod = 1
+    for k in m["mulP_chain_scalars"]:
+        prod = prod * int.from_bytes(H(k), "little") % O.N
+    got = fq.MUL_base(fq.curve4q.pack_scalars([prod]))
+    P = O.xy_from_bytes(H(m["mulP_affine"]))
+    assert bytes(got[0]) == O.encode(P[0], P[1])
+    # [2^1000]G and the addition KAT (curve4q.py:516-547), via scalars
+    for name, k in (("doubleP_affine", pow(2, 1000, O.N)), ("P1000_affine", 1002)):
+        P = O.xy_from_bytes(H(m[name]))
+        assert bytes(fq.MUL_base(fq.curve4q.pack_scalars([k]))[0]) == O.encode(P[0], P[1])
+
+
+def test_strict_mode_raises_reference_messages(fq, golden):
+    c = golden["codec"]
+    bad = [r for r in c["decode"] if r[1] == 4][0]
+    with pytest.raises(Exception, match="Point not on curve"):
+        fq.decode(R([H(bad[0])]), strict=True)
+    quirk = [r for r in c["decode"] if r[1] == 3][0]
+    with pytest.raises(AttributeError):
+        fq.decode(R([H(quirk[0])]), strict=True)
+    with pytest.raises(Exception, match="neutral point"):
+        fq.DH_base(fq.curve4q.pack_scalars([O.N]), strict=True)
+
+
+def test_x25519_golden_and_rfc(fq, golden):
+    rows = golden["x25519"]["x25519"]
+    got = fq.x25519(R([H(r[0]) for r in rows]), R([H(r[1]) for r in rows]))
+    assert hexrows(got) == [r[2] for r in rows]
+    k = u = R([bytes([9] + [0] * 31)])
+    for i in range(1000):                        # RFC 7748 5.2, curve25519.py:104-124
+        k, u = fq.x25519(k, u), k
+        if i == 0:
+            assert bytes(k[0]).hex() == "422c8e7a6227d7bca1350b3e2bb7279f7897b87bb6854b783c60e80311ae3079"
+    assert bytes(k[0]).hex() == "684cf59ba83309552800ef566f2f4d3c1c3887c49360e3875f2eb94d99532c51"
+
+
+# ---------------------------------------------------------------- seeded random vs the oracle
+
+def _oracle_fp2(args):
+    op, a, b = args
+    return O.row_fp2(op, a, b)
+
+
+def _oracle_dh(args):
+    return O.row_dh(*args)
+
+
+def _oracle_mul_base(k):
+    return O.row_mul_base(k)
+
+
+def _pool():
+    return mp.get_context("fork").Pool(min(16, os.cpu_count() or 1))
+
+
+def test_fp2_random_65536_vs_oracle(fq):
+    rng = np.random.default_rng(2)
+    n = 1 << 16
+    a = rng.integers(0, 256, (n, 32), np.uint8); b = rng.integers(0, 256, (n, 32), np.uint8)
+    edge = [0, 1, O.P127 - 1, O.P127, O.P127 + 1, 1 << 127, (1 << 128) - 1, (1 << 64) - 1, (1 << 64) + 1]
+    i = 0
+    for x in edge:
+        for y in edge:
+            a[i] = np.frombuffer(x.to_bytes(16, "little") + y.to_bytes(16, "little"), np.uint8)
+            b[i] = np.frombuffer(y.to_bytes(16, "little") + x.to_bytes(16, "little"), np.uint8)
+            i += 1
+    with _pool() as pool:
+        for op in ("mul", "sqr", "add", "sub"):
+            got = getattr(fq.GFp2, op)(a, b) if op in ("mul", "add", "sub") else fq.GFp2.sqr(a)
+            want = pool.map(_oracle_fp2, [(op, bytes(a[j]), bytes(b[j])) for j in range(n)], chunksize=2048)
+            assert [bytes(r) for r in got] == want, op
+        got = fq.GFp2.inv(a[:4096])
+        want = pool.map(_oracle_fp2, [("inv", bytes(a[j]), None) for j in range(4096)], chunksize=256)
+        assert [bytes(r) for r in got] == want
+
+
+def test_dh_random_4096_vs_oracle(fq):
+    rng = np.random.default_rng(3)
+    n = 4096
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    pub = fq.MUL_base(np.random.default_rng(4).integers(0, 256, (n, 32), np.uint8))
+    pub[::7] = rng.integers(0, 256, (len(pub[::7]), 32), np.uint8)      # arbitrary strings: ~half fail to decode
+    out, st = fq.DH(k, pub)
+    with _pool() as pool:
+        want = pool.map(_oracle_dh, [(bytes(k[j]), bytes(pub[j])) for j in range(n)], chunksize=32)
+        assert [(bytes(o), int(s)) for o, s in zip(out, st)] == want
+        kb = rng.integers(0, 256, (1024, 32), np.uint8)
+        assert [bytes(r) for r in fq.MUL_base(kb)] == pool.map(_oracle_mul_base, [bytes(r) for r in kb], chunksize=16)
+
+
+# ---------------------------------------------------------------- BASELINE sizes: properties that need no oracle
+
+def test_full_size_properties_2_20(fq):
+    n = 1 << 20
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (n, 32), np.uint8); b = rng.integers(0, 256, (n, 32), np.uint8)
+    A, sa = fq.DH_base(a); Bp, sb = fq.DH_base(b)                       # [392a]G, [392b]G
+    assert not sa.any() and not sb.any()
+    AB, s1 = fq.DH(a, Bp); BA, s2 = fq.DH(b, A)                         # DH symmetry (curve4q.py:725-738)
+    assert not s1.any() and not s2.any()
+    assert (AB == BA).all()
+    # fixed base == variable base on G (curve4q.py:743-762)
+    Genc = np.tile(np.frombuffer(O.encode(O.GX, O.GY), np.uint8), (n, 1))
+    viaG, s3 = fq.DH(a, Genc)
+    assert not s3.any() and (viaG == A).all()
+    # encode(decode(x)) round trip on 2^20 valid points, and every row of the batch is distinct work
+    XY, s4 = fq.decode(A)
+    assert not s4.any() and (fq.encode(XY) == A).all()
+    # field identities at size: (a*b)*inv(b) == a for invertible b; a^2 == a*a
+    fa = a.copy(); fb = b.copy(); fa[:, 15] &= 0x7F; fa[:, 31] &= 0x7F; fb[:, 15] &= 0x7F; fb[:, 31] &= 0x7F
+    prod = fq.GFp2.mul(fa, fb)
+    assert (fq.GFp2.sqr(fa) == fq.GFp2.mul(fa, fa)).all()
+    assert (fq.GFp2.mul(prod, fq.GFp2.inv(fb)) == fq.GFp2.mul(fa, fq.GFp2.mul(fb, fq.GFp2.inv(fb)))).all()
+
+
+def test_ragged_and_empty_batches(fq):
+    rng = np.random.default_rng(6)
+    assert fq.MUL_base(np.zeros((0, 32), np.uint8)).shape == (0, 32)
+    out, st = fq.DH(np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8))
+    assert out.shape == (0, 32) and st.shape == (0,)
+    k = rng.integers(0, 256, ((1 << 17) + 131, 32), np.uint8)            # crosses a chunk boundary, not a multiple of 128
+    full = fq.MUL_base(k)
+    for n in (1, 31, 127, 129, 1000):
+        assert (fq.MUL_base(k[:n]) == full[:n]).all()
+    assert (fq.MUL_base(k[-200:]) == full[-200:]).all()
+    # non-contiguous input is accepted (copied)
+    assert (fq.MUL_base(k[::2][:64]) == full[::2][:64]).all()
+
+
+def test_pinned_host_buffers(fq):
+    rng = np.random.default_rng(8)
+    k = fq.pinned_empty((5000, 32)); k[:] = rng.integers(0, 256, (5000, 32), np.uint8)
+    assert (fq.MUL_base(k) == fq.MUL_base(np.array(k))).all()
+
+
+def test_multi_gpu_slices_match_single(fq):
+    if fq.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(9)
+    k = rng.integers(0, 256, (100001, 32), np.uint8)
+    assert (fq.MUL_base(k, ndev=2) == fq.MUL_base(k, ndev=1)).all()

@@ -150,3 +150,19 @@ def test_dh_golden(sim, golden):
     sim.sim_dh_affine(_p(k), _p(xy), _p(out), _p(st), ctypes.c_size_t(n))
     for i, (kk, pp, want_st, want) in enumerate(rows):
         assert (int(st[i]), bytes(out[64 * i:64 * i + 64]).hex()) == (want_st, want), (kk, pp)
+
+
+def test_x25519_golden_and_rfc(sim, golden):
+    rows = golden["x25519"]["x25519"]
+    k = _rows([H(r[0]) for r in rows]); u = _rows([H(r[1]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8)
+    sim.sim_x25519(_p(k), _p(u), _p(out), ctypes.c_size_t(len(rows)))
+    assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[2] for r in rows]
+    # RFC 7748 5.2 iteration vector (curve25519.py:104-124): 1 and 1000 iterations
+    kk = uu = bytes([9] + [0] * 31)
+    for i in range(1000):
+        a = np.frombuffer(kk, np.uint8).copy(); b = np.frombuffer(uu, np.uint8).copy(); o = np.zeros(32, np.uint8)
+        sim.sim_x25519(_p(a), _p(b), _p(o), ctypes.c_size_t(1))
+        kk, uu = bytes(o), kk
+        if i == 0:
+            assert kk.hex() == "422c8e7a6227d7bca1350b3e2bb7279f7897b87bb6854b783c60e80311ae3079"
+    assert kk.hex() == "684cf59ba83309552800ef566f2f4d3c1c3887c49360e3875f2eb94d99532c51"
