@@ -214,12 +214,13 @@ def main():
     # ---- end-to-end arm through the public API from pinned host memory: `e2e`
     pk = fq.pinned_empty((rows, 32)); pk[:] = k
     pp = fq.pinned_empty((rows, 32)); pp[:] = pub
+    po = fq.pinned_empty((rows, 32)); ps = fq.pinned_empty((rows,))
     for _ in range(2):
-        fq.DH(pk, pp)
+        fq.DH(pk, pp, out=po, status=ps)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_e2e, st_e2e = fq.DH(pk, pp)                  # H2D of k and pub, kernels, D2H of out and status: every step
+        out_e2e, st_e2e = fq.DH(pk, pp, out=po, status=ps)   # H2D of k and pub, kernels, D2H of out and status: every step
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * rows * args.steps / e2e_s
@@ -261,7 +262,7 @@ def main():
                            "timing": "CUDA events around each kernel launch, summed over steps, max over ranks", "wall_s_timed_region": wall},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * rows, "d2h_bytes_per_step": 33 * rows,
-                        "note": "fourq_b200.DH(k, B) on pinned numpy arrays, wall clock, per GPU bytes"},
+                        "note": "fourq_b200.DH(k, B, out=, status=) on pinned numpy arrays (inputs and outputs), wall clock, per GPU bytes"},
                 "gpu_launches": args.steps,
                 "roofline": roofline, "cpu_baseline": cpu}
     barrier()

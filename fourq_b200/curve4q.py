@@ -34,6 +34,15 @@ Gx = (0x1A3472237C2FB305286592AD7B3833AA, 0x1E1F553F2878AA9C96869FB360AC77F6)
 Gy = (0x0E3FEE9BA120785AB924A2462BCBB287, 0x6E1C4AF8630E024249A7C344844C8B5C)
 
 
+def _buf(arr, shape, name):
+    """Caller-provided output buffer (e.g. pinned memory from fourq_b200.pinned_empty) or a fresh array."""
+    if arr is None:
+        return np.empty(shape, np.uint8)
+    if not isinstance(arr, np.ndarray) or arr.dtype != np.uint8 or arr.shape != tuple(shape) or not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("%s must be a C-contiguous uint8 array of shape %r" % (name, tuple(shape)))
+    return arr
+
+
 def _raise_first(status):
     bad = np.flatnonzero(status)
     if bad.size:
@@ -42,66 +51,66 @@ def _raise_first(status):
         raise exc("%s (row %d)" % (STATUS_MESSAGES[st], int(bad[0])))
 
 
-def encode(XY, ndev=1):
+def encode(XY, ndev=1, out=None):
     XY = _lib.rows(XY, 64, "XY")
-    out = np.empty((XY.shape[0], 32), np.uint8)
+    out = _buf(out, (XY.shape[0], 32), "out")
     _lib.check(_lib.lib().fq_encode(_lib.ptr(XY), _lib.ptr(out), XY.shape[0], ndev))
     return out
 
 
-def decode(B, ndev=1, strict=False):
+def decode(B, ndev=1, strict=False, out=None, status=None):
     B = _lib.rows(B, 32, "B")
     n = B.shape[0]
-    XY = np.empty((n, 64), np.uint8)
-    status = np.empty(n, np.uint8)
+    XY = _buf(out, (n, 64), "out")
+    status = _buf(status, (n,), "status")
     _lib.check(_lib.lib().fq_decode(_lib.ptr(B), _lib.ptr(XY), _lib.ptr(status), n, ndev))
     if strict:
         _raise_first(status)
     return XY, status
 
 
-def DH(k, B, ndev=1, strict=False):
+def DH(k, B, ndev=1, strict=False, out=None, status=None):
     k = _lib.rows(k, 32, "k")
     B = _lib.rows(B, 32, "B")
     if k.shape[0] != B.shape[0]:
         raise ValueError("k and B must have the same number of rows")
     n = k.shape[0]
-    out = np.empty((n, 32), np.uint8)
-    status = np.empty(n, np.uint8)
+    out = _buf(out, (n, 32), "out")
+    status = _buf(status, (n,), "status")
     _lib.check(_lib.lib().fq_dh(_lib.ptr(k), _lib.ptr(B), _lib.ptr(out), _lib.ptr(status), n, ndev))
     if strict:
         _raise_first(status)
     return out, status
 
 
-def DH_windowed(k, XY, ndev=1, strict=False):
+def DH_windowed(k, XY, ndev=1, strict=False, out=None, status=None):
     k = _lib.rows(k, 32, "k")
     XY = _lib.rows(XY, 64, "XY")
     if k.shape[0] != XY.shape[0]:
         raise ValueError("k and XY must have the same number of rows")
     n = k.shape[0]
-    out = np.empty((n, 64), np.uint8)
-    status = np.empty(n, np.uint8)
+    out = _buf(out, (n, 64), "out")
+    status = _buf(status, (n,), "status")
     _lib.check(_lib.lib().fq_dh_affine(_lib.ptr(k), _lib.ptr(XY), _lib.ptr(out), _lib.ptr(status), n, ndev))
     if strict:
         _raise_first(status)
     return out, status
 
 
-def DH_base(k, ndev=1, strict=False):
+def DH_base(k, ndev=1, strict=False, out=None, status=None):
     k = _lib.rows(k, 32, "k")
     n = k.shape[0]
-    out = np.empty((n, 32), np.uint8)
-    status = np.empty(n, np.uint8)
+    out = _buf(out, (n, 32), "out")
+    status = _buf(status, (n,), "status")
     _lib.check(_lib.lib().fq_dh_base(_lib.ptr(k), _lib.ptr(out), _lib.ptr(status), n, ndev))
     if strict:
         _raise_first(status)
     return out, status
 
 
-def MUL_base(k, ndev=1):
+def MUL_base(k, ndev=1, out=None):
     k = _lib.rows(k, 32, "k")
-    out = np.empty((k.shape[0], 32), np.uint8)
+    out = _buf(out, (k.shape[0], 32), "out")
     _lib.check(_lib.lib().fq_mul_base(_lib.ptr(k), _lib.ptr(out), k.shape[0], ndev))
     return out
 
