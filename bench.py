@@ -36,9 +36,10 @@ sys.path.insert(0, ROOT)
 METRIC = "curve4q_variable_base_dh_scalar_mults_per_s"
 UNIT = "scalar-mults/s"
 ROWS_PER_GPU = 1 << 20
-IMADS_PER_ROW = 103836          # cfg 3 decode + DH_windowed + encode, tight count
+# SURVEY.md 8d, tight counts of 32x32->64 multiply-adds per row of cfg 3 for the algorithm that is run
+IMADS_PER_ROW = {"windowed": 103836, "endo": 58284}
 BYTES_PER_ROW = 96              # 32 scalar + 32 point + 32 out
-WORKLOAD = "cfg3 variable-base DH (decode+validate+[392]P+fixed-window [k]Q+inversion+encode), 2^20 (scalar, encoded point) rows per GPU"
+WORKLOAD = "cfg3 variable-base DH (decode+validate+[392]P+[k]Q+inversion+encode), 2^20 (scalar, encoded point) rows per GPU"
 
 
 def shard_bounds(n, world, rank):
@@ -152,6 +153,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default 2^20, the BASELINE size)")
+    ap.add_argument("--algorithm", default="endo", choices=["windowed", "endo"],
+                    help="scalar-multiplication algorithm of the reference: MUL_windowed or MUL_endo (same outputs)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="rows of the CPU baseline sample (default 256 per core; 0 = skip)")
     args = ap.parse_args()
 
@@ -188,13 +191,15 @@ def main():
     rows = args.rows
     k, pub = make_inputs(fq, rows, rank)
 
+    devop = "dh_endo" if args.algorithm == "endo" else "dh"
+    imads = IMADS_PER_ROW[args.algorithm]
     # ---- device-resident arm: `value`
     dk = fqdev.DeviceBuffer.from_host(local_rank, k)
     dp = fqdev.DeviceBuffer.from_host(local_rank, pub)
     dout = fqdev.DeviceBuffer(local_rank, rows * 32)
     dst = fqdev.DeviceBuffer(local_rank, rows)
     for _ in range(args.warmup):
-        fqdev.dev_run("dh", local_rank, dk, dp, dout, dst, rows)
+        fqdev.dev_run(devop, local_rank, dk, dp, dout, dst, rows)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -202,7 +207,7 @@ def main():
     kernel_ms = []
     for _ in range(args.steps):
         fqdev.flush_l2(local_rank)                       # untimed: write 256 MiB > L2 between timed iterations
-        kernel_ms.append(fqdev.dev_run("dh", local_rank, dk, dp, dout, dst, rows))   # CUDA events on the launch stream
+        kernel_ms.append(fqdev.dev_run(devop, local_rank, dk, dp, dout, dst, rows))   # CUDA events on the launch stream
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -216,11 +221,11 @@ def main():
     pp = fq.pinned_empty((rows, 32)); pp[:] = pub
     po = fq.pinned_empty((rows, 32)); ps = fq.pinned_empty((rows,))
     for _ in range(2):
-        fq.DH(pk, pp, out=po, status=ps)
+        fq.DH(pk, pp, out=po, status=ps, algorithm=args.algorithm)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_e2e, st_e2e = fq.DH(pk, pp, out=po, status=ps)   # H2D of k and pub, kernels, D2H of out and status: every step
+        out_e2e, st_e2e = fq.DH(pk, pp, out=po, status=ps, algorithm=args.algorithm)   # H2D of k and pub, kernels, D2H of out and status: every step
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * rows * args.steps / e2e_s
@@ -230,7 +235,7 @@ def main():
     line = None
     if rank == 0:
         wide_peak, imad_peak = fqdev.imad_peak(local_rank)
-        achieved = (value / world) * IMADS_PER_ROW
+        achieved = (value / world) * imads
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -241,7 +246,7 @@ def main():
                     "traffic": None,
                     "note": "per GPU; achieved = rows/s x %d algorithmic 32x32->64 multiply-adds per row (SURVEY 8d); peak = IMAD.WIDE.U32 "
                             "issue rate measured live by fq_imad_peak (32-bit IMAD measured %.2f T/s); HBM is not the bound: "
-                            "%d B/row -> %.4f of %s %.1f GB/s" % (IMADS_PER_ROW, imad_peak / 1e12, BYTES_PER_ROW,
+                            "%d B/row -> %.4f of %s %.1f GB/s" % (imads, imad_peak / 1e12, BYTES_PER_ROW,
                                                                    (value / world) * BYTES_PER_ROW / 1e9 / hbm,
                                                                    "measured" if peaks else "fallback", hbm)}
         cores = os.cpu_count() or 1
@@ -258,7 +263,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rows_per_gpu": rows, "l2": "flushed (256 MiB memset) between timed iterations",
+                "config": {"workload": WORKLOAD, "algorithm": "MUL_%s (curve4q.py:%s)" % (args.algorithm, "405-442" if args.algorithm == "endo" else "188-235"),
+                           "rows_per_gpu": rows, "l2": "flushed (256 MiB memset) between timed iterations",
                            "timing": "CUDA events around each kernel launch, summed over steps, max over ranks", "wall_s_timed_region": wall},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * rows, "d2h_bytes_per_step": 33 * rows,

@@ -78,10 +78,10 @@ OpDesc describe(int op) {
     case FQ_DEVOP_FP2_INV: return {op, 32, 0, 32, false, (size_t)1 << 18};
     case FQ_DEVOP_DECODE: return {op, 32, 0, 64, true, (size_t)1 << 18};
     case FQ_DEVOP_ENCODE: return {op, 64, 0, 32, false, (size_t)1 << 20};
-    case FQ_DEVOP_DH: return {op, 32, 32, 32, true, (size_t)1 << 17};
-    case FQ_DEVOP_DH_AFFINE: return {op, 32, 64, 64, true, (size_t)1 << 17};
-    case FQ_DEVOP_DH_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
-    case FQ_DEVOP_MUL_BASE: return {op, 32, 0, 32, false, (size_t)1 << 17};
+    case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, 32, 32, 32, true, (size_t)1 << 17};
+    case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, (size_t)1 << 17};
+    case FQ_DEVOP_DH_BASE: case FQ_DEVOP_DH_ENDO_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
+    case FQ_DEVOP_MUL_BASE: case FQ_DEVOP_MUL_ENDO_BASE: return {op, 32, 0, 32, false, (size_t)1 << 17};
     case FQ_DEVOP_X25519: return {op, 32, 32, 32, false, (size_t)1 << 17};
     default: return {-1, 0, 0, 0, false, 0};
   }
@@ -98,10 +98,14 @@ cudaError_t launch(int op, const void* a, const void* b, void* out, void* status
     case FQ_DEVOP_FP2_CONJ: return fqk_fp2_op(FQK_CONJ, a, b, out, n, s);
     case FQ_DEVOP_DECODE: return fqk_decode(a, out, status, n, s);
     case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
-    case FQ_DEVOP_DH: return fqk_dh(0, a, b, out, status, n, s);
-    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, a, b, out, status, n, s);
-    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, a, out, status, n, s);
-    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, a, out, nullptr, n, s);
+    case FQ_DEVOP_DH: return fqk_dh(0, 0, a, b, out, status, n, s);
+    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, a, b, out, status, n, s);
+    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, a, out, status, n, s);
+    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, a, out, nullptr, n, s);
+    case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, a, b, out, status, n, s);
+    case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, a, b, out, status, n, s);
+    case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, a, out, status, n, s);
+    case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, a, out, nullptr, n, s);
     case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, s);
     default: return cudaErrorInvalidValue;
   }
@@ -204,6 +208,10 @@ int fq_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* 
 int fq_dh_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_BASE, k, nullptr, enc_out, status, n, ndev); }
 int fq_mul_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_BASE, k, nullptr, enc_out, nullptr, n, ndev); }
 
+int fq_dh_endo(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO, k, enc_pt, enc_out, status, n, ndev); }
+int fq_dh_endo_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_AFFINE, k, xy, xy_out, status, n, ndev); }
+int fq_dh_endo_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_BASE, k, nullptr, enc_out, status, n, ndev); }
+int fq_mul_endo_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_ENDO_BASE, k, nullptr, enc_out, nullptr, n, ndev); }
 int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_X25519, k, u, out, nullptr, n, ndev); }
 
 int fq_host_alloc(void** p, size_t bytes) {

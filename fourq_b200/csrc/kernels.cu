@@ -6,7 +6,7 @@
 #define FQ_DH_THREADS 128
 #define FQ_DH_SMEM (56 * 16 * FQ_DH_THREADS)       // 7 table entries x 8 quads x 16 B per thread
 
-__constant__ u32 c_base_tabs[512];                  // table_windowed(G) | table_windowed([392]G)
+__constant__ u32 c_base_tabs[1024];                 // table_windowed(G) | table_windowed([392]G) | table_endo(G) | table_endo([392]G)
 
 __device__ __forceinline__ void ld8(const void* base, size_t row, u32* w) {
   const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * row;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_
 }
 
 // variable-base DH.  AFFINE = false: fq_dh (32 B encoded point in, 32 B out); true: fq_dh_affine (64 B in, 64 B out)
-template <bool AFFINE> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
+template <bool AFFINE, bool ENDO> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
 k_dh(const void* k, const void* pt, void* out, unsigned char* status, size_t n) {
   extern __shared__ uint4 smem[];
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,24 +58,24 @@ k_dh(const void* k, const void* pt, void* out, unsigned char* status, size_t n) 
   if (AFFINE) {
     u32 wi[16], wo[16];
     ld8(pt, 2 * row, wi); ld8(pt, 2 * row + 1, wi + 8);
-    status[row] = (unsigned char)row_dh_affine(wk, wi, wo, T);
+    status[row] = (unsigned char)row_dh_affine<ENDO>(wk, wi, wo, T);
     st8(out, 2 * row, wo); st8(out, 2 * row + 1, wo + 8);
   } else {
     u32 we[8], wo[8];
     ld8(pt, row, we);
-    status[row] = (unsigned char)row_dh(wk, we, wo, T);
+    status[row] = (unsigned char)row_dh<ENDO>(wk, we, wo, T);
     st8(out, row, wo);
   }
 }
 
 // fixed base: [k]G (DH = false) or [k][392]G with neutral rejection (DH = true); table in the constant bank
-template <bool DH> __global__ void __launch_bounds__(256)
+template <bool DH, bool ENDO> __global__ void __launch_bounds__(256)
 k_fixed_base(const void* k, void* out, unsigned char* status, size_t n) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   u32 wk[8], wo[8];
   ld8(k, row, wk);
-  u32 st = row_fixed_base<DH>(wk, c_base_tabs + (DH ? 256 : 0), wo);
+  u32 st = row_fixed_base<DH, ENDO>(wk, c_base_tabs + (ENDO ? 512 : 0) + (DH ? 256 : 0), wo);
   if (status) status[row] = (unsigned char)st;
   st8(out, row, wo);
 }
@@ -110,14 +110,16 @@ static inline unsigned grid_for(size_t n, unsigned threads) { return (unsigned)(
 
 cudaError_t fqk_device_init(cudaStream_t s) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_dh<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_dh<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_dh<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_dh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_dh<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_dh<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
   u32* tabs = nullptr; uint4* scratch = nullptr;
-  if ((e = cudaMalloc(&tabs, 512 * sizeof(u32))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&tabs, 1024 * sizeof(u32))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&scratch, 56 * sizeof(uint4))) != cudaSuccess) { cudaFree(tabs); return e; }
   k_build_base_tables<<<1, 1, 0, s>>>(tabs, scratch);
   e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_base_tabs, tabs, 512 * sizeof(u32), 0, cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_base_tabs, tabs, 1024 * sizeof(u32), 0, cudaMemcpyDeviceToDevice, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFree(tabs); cudaFree(scratch);
   return e;
@@ -148,18 +150,24 @@ cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s) {
   k_encode<<<grid_for(n, 256), 256, 0, s>>>(xy, enc, n);
   return cudaGetLastError();
 }
-cudaError_t fqk_dh(int affine, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s) {
+cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   unsigned g = grid_for(n, FQ_DH_THREADS);
-  if (affine) k_dh<true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, (unsigned char*)status, n);
-  else k_dh<false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, (unsigned char*)status, n);
+  unsigned char* st = (unsigned char*)status;
+  if (affine && endo) k_dh<true, true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
+  else if (affine) k_dh<true, false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
+  else if (endo) k_dh<false, true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
+  else k_dh<false, false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
   return cudaGetLastError();
 }
-cudaError_t fqk_fixed_base(int dh, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
+cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   unsigned g = grid_for(n, 256);
-  if (dh) k_fixed_base<true><<<g, 256, 0, s>>>(k, out, (unsigned char*)status, n);
-  else k_fixed_base<false><<<g, 256, 0, s>>>(k, out, (unsigned char*)status, n);
+  unsigned char* st = (unsigned char*)status;
+  if (dh && endo) k_fixed_base<true, true><<<g, 256, 0, s>>>(k, out, st, n);
+  else if (dh) k_fixed_base<true, false><<<g, 256, 0, s>>>(k, out, st, n);
+  else if (endo) k_fixed_base<false, true><<<g, 256, 0, s>>>(k, out, st, n);
+  else k_fixed_base<false, false><<<g, 256, 0, s>>>(k, out, st, n);
   return cudaGetLastError();
 }
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s) {

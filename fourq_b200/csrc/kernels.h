@@ -9,7 +9,7 @@ cudaError_t fqk_device_init(cudaStream_t s);   // once per device: fixed-base ta
 cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_decode(const void* enc, void* xy, void* status, size_t n, cudaStream_t s);
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s);
-cudaError_t fqk_dh(int affine, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s);
-cudaError_t fqk_fixed_base(int dh, const void* k, void* out, void* status, size_t n, cudaStream_t s);
+cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s);
+cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s);
 cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s);

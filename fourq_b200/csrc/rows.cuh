@@ -3,7 +3,7 @@
 // Byte conventions (include/fourq_b200.h): GF(p^2) element = LE128(re)|LE128(im); affine point = x|y (64 B);
 // encoded point and scalar = 32 B.  Words are the little-endian u32 view of those bytes.
 #pragma once
-#include "dh.cuh"
+#include "endo.cuh"
 
 // any two 128-bit values -> tight GF(p^2) element (the reference's ops accept unreduced ints: fields.py:157-181)
 FQ_FN fp2 row_load_fp2(const u32* w) {
@@ -51,26 +51,27 @@ FQ_FN void row_encode(const u32* xy, u32* enc) {
 
 FQ_FN void row_zero(u32* w, int n) { for (int i = 0; i < n; i++) w[i] = 0; }
 
-// fq_dh: decode(enc) -> DH_windowed -> encode
-FQ_FN u32 row_dh(const u32* k, const u32* enc, u32* out, const TabView& T) {
+// fq_dh / fq_dh_endo: decode(enc) -> DH_windowed | DH_endo -> encode
+template <bool ENDO> FQ_FN u32 row_dh(const u32* k, const u32* enc, u32* out, const TabView& T) {
   fp2 x, y, ox, oy;
   u32 st = pt_decode(enc, x, y);
-  if (st == FQ_ST_OK) st = dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
+  if (st == FQ_ST_OK) st = ENDO ? dh_variable_base_endo(row_load_scalar(k), x, y, T, ox, oy) : dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
   if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);
   return st;
 }
-// fq_dh_affine: DH_windowed on an affine point (64 B in, 64 B out)
-FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* out, const TabView& T) {
+// fq_dh_affine / fq_dh_endo_affine: DH_windowed | DH_endo on an affine point (64 B in, 64 B out)
+template <bool ENDO> FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* out, const TabView& T) {
   fp2 x = fp2_canon(row_load_fp2(xy)), y = fp2_canon(row_load_fp2(xy + 8)), ox, oy;
   u32 st = pt_on_curve(x, y) ? FQ_ST_OK : FQ_ST_NOT_ON_CURVE;                       // curve4q.py:447
-  if (st == FQ_ST_OK) st = dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
+  if (st == FQ_ST_OK) st = ENDO ? dh_variable_base_endo(row_load_scalar(k), x, y, T, ox, oy) : dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
   if (st == FQ_ST_OK) { row_store_fp2(out, ox); row_store_fp2(out + 8, oy); } else row_zero(out, 16);
   return st;
 }
 // fq_mul_base (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base (true): encode([k][392]G) with the neutral check
-template <bool CHECK_NEUTRAL> FQ_FN u32 row_fixed_base(const u32* k, const u32* tab, u32* out) {
+template <bool CHECK_NEUTRAL, bool ENDO> FQ_FN u32 row_fixed_base(const u32* k, const u32* tab, u32* out) {
   fp2 ox, oy;
-  mul_fixed_base(row_load_scalar(k), tab, ox, oy);
+  if (ENDO) { SelectConst sel; sel.tab = tab; pt_to_affine(mul_endo(row_load_scalar(k), sel), ox, oy); }
+  else mul_fixed_base(row_load_scalar(k), tab, ox, oy);
   u32 st = FQ_ST_OK;
   if (CHECK_NEUTRAL && (fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one()))) st = FQ_ST_NEUTRAL;
   if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);
@@ -78,12 +79,12 @@ template <bool CHECK_NEUTRAL> FQ_FN u32 row_fixed_base(const u32* k, const u32* 
 }
 
 // Fixed-base tables: out[0..255] = table_windowed(G) (curve4q.py:582), out[256..511] = table_windowed([392]G)
-// (curve4q.py:758-759).  scratch: 56 uint4.
+// (curve4q.py:758-759), out[512..767] = table_endo(G), out[768..1023] = table_endo([392]G) (curve4q.py:760).  scratch: 56 uint4.
 FQ_FN void row_build_base_tables(u32* out, uint4* scratch) {
   TabView T; T.base = scratch; T.stride = 1;
-  for (int which = 0; which < 2; which++) {
-    ptR1 B = (which == 0) ? pt_from_affine(curve_gx(), curve_gy()) : pt_clear_cofactor(curve_gx(), curve_gy());
-    ptR2 T7 = tab_build(T, B);
+  for (int which = 0; which < 4; which++) {
+    ptR1 B = ((which & 1) == 0) ? pt_from_affine(curve_gx(), curve_gy()) : pt_clear_cofactor(curve_gx(), curve_gy());
+    ptR2 T7 = (which < 2) ? tab_build(T, B) : endo_tab_build(T, B);
     for (int e = 0; e < 7; e++) { ptR2 P = tab_load(T, e); r2_to_words(P, out + which * 256 + e * 32); }
     r2_to_words(T7, out + which * 256 + 7 * 32);
   }

@@ -7,10 +7,11 @@
 #include <cstddef>
 #include "../../fourq_b200/csrc/rows.cuh"
 #include "../../fourq_b200/csrc/x25519.cuh"
+#include "../../fourq_b200/csrc/endo.cuh"
 
 namespace fqsim { thread_local u32 cc = 0; }
 
-static u32 g_tabs[512];
+static u32 g_tabs[1024];
 static bool g_tabs_ready = false;
 static void ensure_tabs() {
   if (!g_tabs_ready) { uint4 scratch[56]; row_build_base_tables(g_tabs, scratch); g_tabs_ready = true; }
@@ -70,7 +71,7 @@ int sim_dh(const uint8_t* k, const uint8_t* enc, uint8_t* out, uint8_t* status, 
   uint4 tab[56]; TabView T; T.base = tab; T.stride = 1;
   for (size_t i = 0; i < n; i++) {
     u32 wk[8], we[8], wo[8]; memcpy(wk, k + 32 * i, 32); memcpy(we, enc + 32 * i, 32);
-    status[i] = (uint8_t)row_dh(wk, we, wo, T);
+    status[i] = (uint8_t)row_dh<false>(wk, we, wo, T);
     memcpy(out + 32 * i, wo, 32);
   }
   return 0;
@@ -79,16 +80,18 @@ int sim_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* out, uint8_t* st
   uint4 tab[56]; TabView T; T.base = tab; T.stride = 1;
   for (size_t i = 0; i < n; i++) {
     u32 wk[8], wi[16], wo[16]; memcpy(wk, k + 32 * i, 32); memcpy(wi, xy + 64 * i, 64);
-    status[i] = (uint8_t)row_dh_affine(wk, wi, wo, T);
+    status[i] = (uint8_t)row_dh_affine<false>(wk, wi, wo, T);
     memcpy(out + 64 * i, wo, 64);
   }
   return 0;
 }
 int sim_fixed_base(int dh, const uint8_t* k, uint8_t* out, uint8_t* status, size_t n) {
   ensure_tabs();
+  const int endo = dh >> 1; dh &= 1;
   for (size_t i = 0; i < n; i++) {
     u32 wk[8], wo[8]; memcpy(wk, k + 32 * i, 32);
-    u32 st = dh ? row_fixed_base<true>(wk, g_tabs + 256, wo) : row_fixed_base<false>(wk, g_tabs, wo);
+    u32 st = endo ? (dh ? row_fixed_base<true, true>(wk, g_tabs + 768, wo) : row_fixed_base<false, true>(wk, g_tabs + 512, wo))
+                  : (dh ? row_fixed_base<true, false>(wk, g_tabs + 256, wo) : row_fixed_base<false, false>(wk, g_tabs, wo));
     if (status) status[i] = (uint8_t)st;
     memcpy(out + 32 * i, wo, 32);
   }
@@ -101,6 +104,38 @@ int sim_recode(const uint8_t* k, uint8_t* idx, uint8_t* neg, uint8_t* reduced) {
   memcpy(reduced, r.v, 32);
   scal S = scal_digits_init(r);
   for (int i = 0; i < 62; i++) { u32 a, b; scal_next_digit(S, a, b); idx[i] = (uint8_t)a; neg[i] = (uint8_t)(b & 1); }
+  return 0;
+}
+// endomorphism pieces: which 0 = phi, 1 = psi on affine 64-byte points -> affine
+int sim_endo_map(int which, const uint8_t* xy, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wi[16], wo[16]; memcpy(wi, xy + 64 * i, 64);
+    fp2 x = fp2_canon(row_load_fp2(wi)), y = fp2_canon(row_load_fp2(wi + 8)), ox, oy;
+    ptR1 P = pt_from_affine(x, y);
+    ptR1 R = which == 0 ? endo_phi(P) : endo_psi(P);
+    pt_to_affine(R, ox, oy);
+    row_store_fp2(wo, ox); row_store_fp2(wo + 8, oy);
+    memcpy(out + 64 * i, wo, 64);
+  }
+  return 0;
+}
+// decompose: k (32 B) -> 4 x u64; recode: digits idx[65], sign[65] in index order 0..64
+int sim_endo_scalar(const uint8_t* k, uint64_t* v, uint8_t* idx, uint8_t* sign) {
+  u32 wk[8]; memcpy(wk, k, 32);
+  scal4 d = endo_decompose(row_load_scalar(wk));
+  for (int j = 0; j < 4; j++) v[j] = d.v[j];
+  scal S; u32 d64 = endo_recode(d, S);
+  idx[64] = (uint8_t)d64; sign[64] = 1;
+  for (int i = 63; i >= 0; i--) { u32 a, b; endo_next_digit(S, a, b); idx[i] = (uint8_t)a; sign[i] = (uint8_t)((b & 1) ^ 1); }
+  return 0;
+}
+int sim_dh_endo(const uint8_t* k, const uint8_t* enc, uint8_t* out, uint8_t* status, size_t n) {
+  uint4 tab[56]; TabView T; T.base = tab; T.stride = 1;
+  for (size_t i = 0; i < n; i++) {
+    u32 wk[8], we[8], wo[8]; memcpy(wk, k + 32 * i, 32); memcpy(we, enc + 32 * i, 32);
+    status[i] = (uint8_t)row_dh<true>(wk, we, wo, T);
+    memcpy(out + 32 * i, wo, 32);
+  }
   return 0;
 }
 int sim_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n) {

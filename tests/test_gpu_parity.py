@@ -56,15 +56,18 @@ def test_codec_golden(fq, golden):
     assert set(int(s) for s in st) == {0, 1, 2, 3, 4}
 
 
-def test_scalar_mult_golden(fq, golden):
+@pytest.mark.parametrize("alg", ["windowed", "endo"])
+def test_scalar_mult_golden(fq, golden, alg):
+    """MUL_windowed / MUL_endo based entry points: the reference asserts both give the same points (curve4q.py:706-762)."""
     m = golden["mul"]
-    assert hexrows(fq.MUL_base(R([H(r[0]) for r in m["mul_base"]]))) == [r[1] for r in m["mul_base"]]
-    out, st = fq.DH_base(R([H(r[0]) for r in m["dh_base"]]))
+    assert hexrows(fq.MUL_base(R([H(r[0]) for r in m["mul_base"]]), algorithm=alg)) == [r[1] for r in m["mul_base"]]
+    out, st = fq.DH_base(R([H(r[0]) for r in m["dh_base"]]), algorithm=alg)
     assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[1], r[2]) for r in m["dh_base"]]
-    out, st = fq.DH(R([H(r[0]) for r in m["dh"]]), R([H(r[1]) for r in m["dh"]]))
+    out, st = fq.DH(R([H(r[0]) for r in m["dh"]]), R([H(r[1]) for r in m["dh"]]), algorithm=alg)
     assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh"]]
     assert set(int(s) for s in st) == {0, 1, 2, 3, 4, 5}
-    out, st = fq.DH_windowed(R([H(r[0]) for r in m["dh_affine"]]), R([H(r[1]) for r in m["dh_affine"]]))
+    dh_aff = fq.DH_windowed if alg == "windowed" else fq.DH_endo
+    out, st = dh_aff(R([H(r[0]) for r in m["dh_affine"]]), R([H(r[1]) for r in m["dh_affine"]]))
     assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh_affine"]]
 
 
@@ -74,9 +77,10 @@ def test_reference_mulP_chain(fq, golden):
     prod = 1
     for k in m["mulP_chain_scalars"]:
         prod = prod * int.from_bytes(H(k), "little") % O.N
-    got = fq.MUL_base(fq.curve4q.pack_scalars([prod]))
     P = O.xy_from_bytes(H(m["mulP_affine"]))
-    assert bytes(got[0]) == O.encode(P[0], P[1])
+    for alg in ("windowed", "endo"):
+        got = fq.MUL_base(fq.curve4q.pack_scalars([prod]), algorithm=alg)
+        assert bytes(got[0]) == O.encode(P[0], P[1])
     # [2^1000]G and the addition KAT (curve4q.py:516-547), via scalars
     for name, k in (("doubleP_affine", pow(2, 1000, O.N)), ("P1000_affine", 1002)):
         P = O.xy_from_bytes(H(m[name]))
@@ -153,10 +157,12 @@ def test_dh_random_4096_vs_oracle(fq):
     k = rng.integers(0, 256, (n, 32), np.uint8)
     pub = fq.MUL_base(np.random.default_rng(4).integers(0, 256, (n, 32), np.uint8))
     pub[::7] = rng.integers(0, 256, (len(pub[::7]), 32), np.uint8)      # arbitrary strings: ~half fail to decode
-    out, st = fq.DH(k, pub)
+    out, st = fq.DH(k, pub, algorithm="windowed")
+    out2, st2 = fq.DH(k, pub, algorithm="endo")
     with _pool() as pool:
         want = pool.map(_oracle_dh, [(bytes(k[j]), bytes(pub[j])) for j in range(n)], chunksize=32)
         assert [(bytes(o), int(s)) for o, s in zip(out, st)] == want
+        assert [(bytes(o), int(s)) for o, s in zip(out2, st2)] == want
         kb = rng.integers(0, 256, (1024, 32), np.uint8)
         assert [bytes(r) for r in fq.MUL_base(kb)] == pool.map(_oracle_mul_base, [bytes(r) for r in kb], chunksize=16)
 
@@ -167,11 +173,14 @@ def test_full_size_properties_2_20(fq):
     n = 1 << 20
     rng = np.random.default_rng(5)
     a = rng.integers(0, 256, (n, 32), np.uint8); b = rng.integers(0, 256, (n, 32), np.uint8)
-    A, sa = fq.DH_base(a); Bp, sb = fq.DH_base(b)                       # [392a]G, [392b]G
+    A, sa = fq.DH_base(a, algorithm="windowed"); Bp, sb = fq.DH_base(b, algorithm="endo")       # [392a]G, [392b]G
     assert not sa.any() and not sb.any()
-    AB, s1 = fq.DH(a, Bp); BA, s2 = fq.DH(b, A)                         # DH symmetry (curve4q.py:725-738)
+    AB, s1 = fq.DH(a, Bp, algorithm="windowed"); BA, s2 = fq.DH(b, A, algorithm="endo")           # DH symmetry (curve4q.py:725-738)
     assert not s1.any() and not s2.any()
     assert (AB == BA).all()
+    AB2, _ = fq.DH(a, Bp, algorithm="endo")                              # windowed == endo on 2^20 rows (curve4q.py:706-762)
+    assert (AB2 == AB).all()
+    assert (fq.MUL_base(a, algorithm="windowed") == fq.MUL_base(a, algorithm="endo")).all()
     # fixed base == variable base on G (curve4q.py:743-762)
     Genc = np.tile(np.frombuffer(O.encode(O.GX, O.GY), np.uint8), (n, 1))
     viaG, s3 = fq.DH(a, Genc)

@@ -137,6 +137,18 @@ def test_fixed_base_golden(sim, golden):
         assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), kk
 
 
+def test_fixed_base_endo_golden(sim, golden):
+    rows = golden["mul"]["mul_base"]
+    k = _rows([H(r[0]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8)
+    sim.sim_fixed_base(2, _p(k), _p(out), None, ctypes.c_size_t(len(rows)))
+    assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[1] for r in rows]
+    rows = golden["mul"]["dh_base"]
+    k = _rows([H(r[0]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8); st = np.zeros(len(rows), np.uint8)
+    sim.sim_fixed_base(3, _p(k), _p(out), _p(st), ctypes.c_size_t(len(rows)))
+    for i, (kk, want_st, want) in enumerate(rows):
+        assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), kk
+
+
 def test_dh_golden(sim, golden):
     rows = golden["mul"]["dh"]
     k = _rows([H(r[0]) for r in rows]); e = _rows([H(r[1]) for r in rows]); n = len(rows)
@@ -166,3 +178,41 @@ def test_x25519_golden_and_rfc(sim, golden):
         if i == 0:
             assert kk.hex() == "422c8e7a6227d7bca1350b3e2bb7279f7897b87bb6854b783c60e80311ae3079"
     assert kk.hex() == "684cf59ba83309552800ef566f2f4d3c1c3887c49360e3875f2eb94d99532c51"
+
+
+def test_endo_pieces_golden(sim, golden):
+    e = golden["endo"]
+    for which, key in ((0, "phi"), (1, "psi")):
+        rows = e[key]
+        xy = _rows([H(r[0]) for r in rows]); out = np.zeros(64 * len(rows), np.uint8)
+        sim.sim_endo_map(which, _p(xy), _p(out), ctypes.c_size_t(len(rows)))
+        assert [bytes(out[64 * i:64 * i + 64]).hex() for i in range(len(rows))] == [r[1] for r in rows], key
+    for (k, v), (v2, s, d) in zip(e["decompose"], e["recode"]):
+        assert v == v2
+        kb = np.frombuffer(H(k), np.uint8).copy()
+        vv = np.zeros(4, np.uint64); idx = np.zeros(65, np.uint8); sg = np.zeros(65, np.uint8)
+        sim.sim_endo_scalar(_p(kb), _p(vv), _p(idx), _p(sg))
+        assert [int(x) for x in vv] == v, k
+        assert "".join(str(int(x)) for x in sg) == s and "".join(str(int(x)) for x in idx) == d, k
+
+
+def test_endo_scalar_random_vs_oracle(sim):
+    rng = random.Random(21)
+    for _ in range(3000):
+        k = rng.getrandbits(256)
+        kb = np.frombuffer(k.to_bytes(32, "little"), np.uint8).copy()
+        vv = np.zeros(4, np.uint64); idx = np.zeros(65, np.uint8); sg = np.zeros(65, np.uint8)
+        sim.sim_endo_scalar(_p(kb), _p(vv), _p(idx), _p(sg))
+        v = O.decompose(k)
+        assert [int(x) for x in vv] == v
+        s, d = O.recode_endo(v)
+        assert list(sg) == s and list(idx) == d
+
+
+def test_dh_endo_golden(sim, golden):
+    rows = golden["mul"]["dh"]
+    k = _rows([H(r[0]) for r in rows]); e = _rows([H(r[1]) for r in rows]); n = len(rows)
+    out = np.zeros(32 * n, np.uint8); st = np.zeros(n, np.uint8)
+    sim.sim_dh_endo(_p(k), _p(e), _p(out), _p(st), ctypes.c_size_t(n))
+    for i, (kk, ee, want_st, want) in enumerate(rows):
+        assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), (kk, ee)
