@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfourq_b200.so")
-SOURCES = ["kernels.cu", "x25519.cu", "capi.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+SOURCES = ["kernels.cu", "kernels_dh_windowed.cu", "kernels_dh_endo.cu", "x25519.cu", "capi.cu"]
+NVCC_FLAGS = os.environ.get("FQ_NVCC_EXTRA", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-cudart", "static"]
 
 

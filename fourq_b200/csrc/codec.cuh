@@ -35,19 +35,19 @@ FQ_FN u32 pt_decode(const u32* in, fp2& x, fp2& y) {
   u32 y1p = in[4] & in[5] & in[6] & (in[7] | 0x80000000u);
   if (st == FQ_ST_OK && (y0p == 0xffffffffu || y1p == 0xffffffffu)) st = FQ_ST_NONCANONICAL;   // :61
 
-  fp2 y2 = fp2_sqr(y);                                                        // :65
+  fp2 y2 = fp2_sqr_c(y);                                                       // :65
   fp2 u = fp2_sub(y2, fp2_one());                                             // :66
-  fp2 v = fp2_add(fp2_mul(curve_d(), y2), fp2_one());                         // :67
+  fp2 v = fp2_add(fp2_mul_c(curve_d(), y2), fp2_one());                         // :67
   fpb V0 = fp_prep(v.re), V1 = fp_prep(v.im);
   fp t0 = fp_add(fp_mul_prep(u.re, V0), fp_mul_prep(u.im, V1));               // :69
   fp t1 = fp_sub(fp_mul_prep(u.im, V0), fp_mul_prep(u.re, V1));               // :70
   fp t2 = fp_add(fp_sqr(v.re), fp_sqr(v.im));                                 // :71
   fp t3 = fp_add(fp_sqr(t0), fp_sqr(t1));                                     // :72
-  t3 = fp_mul(fp_invsqrt(t3), t3);                                            // :73
+  t3 = fp_mul(fp_invsqrt_c(t3), t3);                                            // :73
   fp t = fp_dbl(fp_add(t0, t3));                                              // :75
   if (st == FQ_ST_OK && fp_is_zero(t)) st = FQ_ST_QUIRK_T0;                   // :76-77 (the reference raises here)
   fpb T2 = fp_prep(t2);
-  fp a = fp_invsqrt(fp_mul(fp_mul_prep(fp_sqr(t2), T2), t));                  // :79
+  fp a = fp_invsqrt_c(fp_mul(fp_mul_prep(fp_sqr(t2), T2), t));                  // :79
   fp at2 = fp_mul_prep(a, T2);
   fp b = fp_mul(at2, t);                                                      // :80
   fp x0 = fp_half(b);                                                         // :82

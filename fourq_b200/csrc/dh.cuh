@@ -52,31 +52,44 @@ FQ_FN ptR2 tab_select(const TabView& T, const ptR2& T7, u32 idx) {
 // curve4q.py:179-185: T[i] = [2i+1]P, i = 0..7; returns T[7]
 FQ_FN ptR2 tab_build(const TabView& T, const ptR1& P) {
   ptR1 P2 = P;
-  pt_dbl(P2);
-  ptR3p P2p = pt_r1_to_r3p(P2);
-  ptR2 Ti = pt_r1_to_r2(P);
+  pt_dbl_c(&P2);
+  ptR3 P23; pt_r1_to_r3_c(&P23, &P2);
+  ptR2 Ti; pt_r1_to_r2_c(&Ti, &P);
   tab_store(T, 0, Ti);
   FQ_NOUNROLL
   for (int i = 1; i < 8; i++) {
-    Ti = pt_r1_to_r2(pt_add_core(P2p, Ti));
+    ptR1 S; pt_add_core_c(&S, &P23, &Ti);
+    pt_r1_to_r2_c(&Ti, &S);
     if (i < 7) tab_store(T, i, Ti);
   }
   return Ti;
 }
 
-// curve4q.py:188-235 with the digits of scalar.cuh.  SELECT(idx) returns T[idx] in constant time.
-template <class SELECT> FQ_FN ptR1 mul_windowed(const scal& k, SELECT select) {
-  scal S = scal_digits_init(scal_reduce_odd(k));
-  ptR1 Q = pt_r2_to_r4(select(0u));                 // digit 62 is always +1
+// The scalar-dependent plan of a multiplication: the packed digit register and the table index of the leading digit.
+struct MulPlan { scal S; u32 first; };
+
+// curve4q.py:216-226
+FQ_FN MulPlan plan_windowed(const scal& k) {
+  MulPlan pl; pl.S = scal_digits_init(scal_reduce_odd(k)); pl.first = 0u;          // digit 62 is always +1
+  return pl;
+}
+// curve4q.py:229-233 with the digits of scalar.cuh.  SELECT(idx) returns T[idx] in constant time.
+template <class SELECT> FQ_FN ptR1 loop_windowed(MulPlan& pl, SELECT select) {
+  ptR1 Q = pt_r2_to_r4(select(pl.first));
   FQ_NOUNROLL
   for (int i = 61; i >= 0; i--) {
     FQ_NOUNROLL
     for (int j = 0; j < 4; j++) pt_dbl(Q);
     u32 idx, neg;
-    scal_next_digit(S, idx, neg);
+    scal_next_digit(pl.S, idx, neg);
     Q = pt_add(Q, pt_r2_cneg(neg, select(idx)));
   }
   return Q;
+}
+// curve4q.py:188-235
+template <class SELECT> FQ_FN ptR1 mul_windowed(const scal& k, SELECT select) {
+  MulPlan pl = plan_windowed(k);
+  return loop_windowed(pl, select);
 }
 
 struct SelectShared {
@@ -84,15 +97,24 @@ struct SelectShared {
   FQ_MFN ptR2 operator()(u32 idx) const { return tab_select(T, T7, idx); }
 };
 
-// DH_core (curve4q.py:446-462) after the point has been validated: [392]P, table, [k]Q, affine, neutral check.
-FQ_FN u32 dh_variable_base(const scal& k, const fp2& x, const fp2& y, const TabView& T, fp2& ox, fp2& oy) {
-  ptR1 Q = pt_clear_cofactor(x, y);
-  SelectShared sel; sel.T = T;
-  sel.T7 = tab_build(T, Q);
-  ptR1 R = mul_windowed(k, sel);
+// DH_core (curve4q.py:446-462) after the point has been validated, in three phases so that a kernel can keep all warps
+// of a CTA in the same phase (instruction-cache locality): setup ([392]P, table, scalar plan), loop ([k]Q), finish
+// (affine, neutral check).
+struct DhState { ptR2 T7; MulPlan plan; };
+
+FQ_FN u32 dh_finish(const ptR1& R, fp2& ox, fp2& oy) {
   pt_to_affine(R, ox, oy);
   bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());      // curve4q.py:459
   return neutral ? FQ_ST_NEUTRAL : FQ_ST_OK;
+}
+FQ_FN void dh_setup_windowed(const scal& k, const fp2& x, const fp2& y, const TabView& T, DhState& D) {
+  ptR1 Q = pt_clear_cofactor(x, y);
+  D.T7 = tab_build(T, Q);
+  D.plan = plan_windowed(k);
+}
+FQ_FN ptR1 dh_loop_windowed(const TabView& T, DhState& D) {
+  SelectShared sel; sel.T = T; sel.T7 = D.T7;
+  return loop_windowed(D.plan, sel);
 }
 
 // fixed base: the table is read-only, shared by all threads (constant bank), 8 entries x 32 words

@@ -25,61 +25,59 @@ FQ_FN fp2 endo_cpsi4() { return fp2_set(fp_set(0xfffffff6u, 0xffffffffu, 0xfffff
 
 struct pt3 { fp2 X, Y, Z; };
 
-FQ_FN fp2 fp2_two_sqr(const fp2& z) { return fp2_dbl(fp2_sqr(z)); }
+FQ_FN fp2 fp2_two_sqr(const fp2& z) { return fp2_dbl(fp2_sqr_c(z)); }
 
 // curve4q.py:258-267
 FQ_FN pt3 endo_tau(const pt3& P) {
-  fp2 A = fp2_sqr(P.X), B = fp2_sqr(P.Y);
+  fp2 A = fp2_sqr_c(P.X), B = fp2_sqr_c(P.Y);
   fp2 C = fp2_add(A, B), D = fp2_sub(A, B);
-  fp2b Dp = fp2_prep(D);
   pt3 R;
-  R.X = fp2_mul_prep(fp2_mul(fp2_mul(endo_ctau(), P.X), P.Y), Dp);
-  R.Y = fp2_neg(fp2_mul(fp2_add(fp2_two_sqr(P.Z), D), C));
-  R.Z = fp2_mul_prep(C, Dp);
+  R.X = fp2_mul_c(fp2_mul_c(fp2_mul_c(endo_ctau(), P.X), P.Y), D);
+  R.Y = fp2_neg(fp2_mul_c(fp2_add(fp2_two_sqr(P.Z), D), C));
+  R.Z = fp2_mul_c(C, D);
   return R;
 }
 // curve4q.py:269-280 -> R1
 FQ_FN ptR1 endo_tau_dual(const pt3& P) {
-  fp2 A = fp2_sqr(P.X), B = fp2_sqr(P.Y);
+  fp2 A = fp2_sqr_c(P.X), B = fp2_sqr_c(P.Y);
   fp2 C = fp2_add(A, B);
   ptR1 R;
   R.Ta = fp2_sub(B, A);
   fp2 D = fp2_sub(fp2_two_sqr(P.Z), R.Ta);
-  R.Tb = fp2_mul(fp2_mul(endo_ctaudual(), P.X), P.Y);
-  fp2b Cp = fp2_prep(C);
-  R.X = fp2_mul_prep(R.Tb, Cp); R.Y = fp2_mul(R.Ta, D); R.Z = fp2_mul_prep(D, Cp);
+  R.Tb = fp2_mul_c(fp2_mul_c(endo_ctaudual(), P.X), P.Y);
+  R.X = fp2_mul_c(R.Tb, C); R.Y = fp2_mul_c(R.Ta, D); R.Z = fp2_mul_c(D, C);
   return R;
 }
 // curve4q.py:282-302
 FQ_FN pt3 endo_upsilon(const pt3& P) {
-  fp2 A = fp2_mul(fp2_mul(endo_cphi0(), P.X), P.Y);
-  fp2 B = fp2_mul(P.Y, P.Z);
-  fp2 C = fp2_sqr(P.Y), D = fp2_sqr(P.Z);
-  fp2 F = fp2_sqr(D), G = fp2_sqr(B), H = fp2_sqr(C);
-  fp2 I = fp2_mul(endo_cphi1(), B);
-  fp2 J = fp2_add(C, fp2_mul(endo_cphi2(), D));
-  fp2 K = fp2_add(fp2_add(fp2_mul(endo_cphi8(), G), H), fp2_mul(endo_cphi9(), F));
+  fp2 A = fp2_mul_c(fp2_mul_c(endo_cphi0(), P.X), P.Y);
+  fp2 B = fp2_mul_c(P.Y, P.Z);
+  fp2 C = fp2_sqr_c(P.Y), D = fp2_sqr_c(P.Z);
+  fp2 F = fp2_sqr_c(D), G = fp2_sqr_c(B), H = fp2_sqr_c(C);
+  fp2 I = fp2_mul_c(endo_cphi1(), B);
+  fp2 J = fp2_add(C, fp2_mul_c(endo_cphi2(), D));
+  fp2 K = fp2_add(fp2_add(fp2_mul_c(endo_cphi8(), G), H), fp2_mul_c(endo_cphi9(), F));
   pt3 R;
-  R.X = fp2_conj(fp2_mul(fp2_mul(A, K), fp2_mul(fp2_add(I, J), fp2_sub(I, J))));
-  fp2 L = fp2_add(C, fp2_mul(endo_cphi4(), D));
-  fp2 M = fp2_mul(endo_cphi3(), B);
-  fp2 Nn = fp2_mul(fp2_add(L, M), fp2_sub(L, M));
-  fp2 Y2 = fp2_add(fp2_add(H, fp2_mul(endo_cphi6(), G)), fp2_mul(endo_cphi7(), F));
-  R.Y = fp2_conj(fp2_mul(fp2_mul(fp2_mul(endo_cphi5(), D), Nn), Y2));
-  R.Z = fp2_conj(fp2_mul(fp2_mul(B, K), Nn));
+  R.X = fp2_conj(fp2_mul_c(fp2_mul_c(A, K), fp2_mul_c(fp2_add(I, J), fp2_sub(I, J))));
+  fp2 L = fp2_add(C, fp2_mul_c(endo_cphi4(), D));
+  fp2 M = fp2_mul_c(endo_cphi3(), B);
+  fp2 Nn = fp2_mul_c(fp2_add(L, M), fp2_sub(L, M));
+  fp2 Y2 = fp2_add(fp2_add(H, fp2_mul_c(endo_cphi6(), G)), fp2_mul_c(endo_cphi7(), F));
+  R.Y = fp2_conj(fp2_mul_c(fp2_mul_c(fp2_mul_c(endo_cphi5(), D), Nn), Y2));
+  R.Z = fp2_conj(fp2_mul_c(fp2_mul_c(B, K), Nn));
   return R;
 }
 // curve4q.py:304-316
 FQ_FN pt3 endo_chi(const pt3& P) {
   fp2 A = fp2_conj(P.X), B = fp2_conj(P.Y);
-  fp2 C = fp2_sqr(fp2_conj(P.Z));
-  fp2 D = fp2_sqr(A);
-  fp2 G = fp2_mul(B, fp2_add(D, fp2_mul(endo_cpsi2(), C)));
-  fp2 H = fp2_neg(fp2_add(D, fp2_mul(endo_cpsi4(), C)));
+  fp2 C = fp2_sqr_c(fp2_conj(P.Z));
+  fp2 D = fp2_sqr_c(A);
+  fp2 G = fp2_mul_c(B, fp2_add(D, fp2_mul_c(endo_cpsi2(), C)));
+  fp2 H = fp2_neg(fp2_add(D, fp2_mul_c(endo_cpsi4(), C)));
   pt3 R;
-  R.X = fp2_mul(fp2_mul(fp2_mul(endo_cpsi1(), A), C), H);
-  R.Y = fp2_mul(G, fp2_add(D, fp2_mul(endo_cpsi3(), C)));
-  R.Z = fp2_mul(G, H);
+  R.X = fp2_mul_c(fp2_mul_c(fp2_mul_c(endo_cpsi1(), A), C), H);
+  R.Y = fp2_mul_c(G, fp2_add(D, fp2_mul_c(endo_cpsi3(), C)));
+  R.Z = fp2_mul_c(G, H);
   return R;
 }
 FQ_FN pt3 pt3_of(const ptR1& P) { pt3 R; R.X = P.X; R.Y = P.Y; R.Z = P.Z; return R; }
@@ -167,46 +165,58 @@ FQ_FN void endo_next_digit(scal& s, u32& idx, u32& neg) {
 // S = psi(phi(P)); entries in R2, 0..6 to shared memory, returns T[7].
 FQ_FN ptR2 endo_tab_build(const TabView& T, const ptR1& P) {
   ptR1 Qp = endo_phi(P);
-  ptR2 T0 = pt_r1_to_r2(P);
+  ptR3 A3;                                   // the left operand of each addition, in R3
+  ptR2 T0, Ti;
+  ptR1 S;
+  pt_r1_to_r2_c(&T0, &P);
   tab_store(T, 0, T0);
-  tab_store(T, 1, pt_r1_to_r2(pt_add_core(pt_r1_to_r3p(Qp), T0)));
-  {
-    ptR3p R3 = pt_r1_to_r3p(endo_psi(P));
-    tab_store(T, 2, pt_r1_to_r2(pt_add_core(R3, T0)));
-    tab_store(T, 3, pt_r1_to_r2(pt_add_core(R3, tab_load(T, 1))));
-  }
-  ptR3p S3 = pt_r1_to_r3p(endo_psi(Qp));
-  ptR2 Ti = T0;
+  pt_r1_to_r3_c(&A3, &Qp);
+  pt_add_core_c(&S, &A3, &T0); pt_r1_to_r2_c(&Ti, &S); tab_store(T, 1, Ti);          // T[1] = Q + P
+  S = endo_psi(P);
+  pt_r1_to_r3_c(&A3, &S);
+  pt_add_core_c(&S, &A3, &Ti); pt_r1_to_r2_c(&Ti, &S); tab_store(T, 3, Ti);          // T[3] = R + T[1]
+  pt_add_core_c(&S, &A3, &T0); pt_r1_to_r2_c(&Ti, &S); tab_store(T, 2, Ti);          // T[2] = R + P
+  S = endo_psi(Qp);
+  pt_r1_to_r3_c(&A3, &S);
   FQ_NOUNROLL
-  for (int i = 0; i < 4; i++) {
-    Ti = pt_r1_to_r2(pt_add_core(S3, tab_load(T, i)));
+  for (int i = 0; i < 4; i++) {                                                       // T[4+i] = S + T[i]
+    Ti = tab_load(T, i);
+    pt_add_core_c(&S, &A3, &Ti); pt_r1_to_r2_c(&Ti, &S);
     if (i < 3) tab_store(T, 4 + i, Ti);
   }
   return Ti;
 }
 
-// curve4q.py:405-442
-template <class SELECT> FQ_FN ptR1 mul_endo(const scal& k, SELECT select) {
-  scal S;
-  u32 d64 = endo_recode(endo_decompose(k), S);
-  ptR1 Q = pt_r2_to_r4(select(d64));                // s[64] = 1: positive
+// curve4q.py:405-436: decompose + recode
+FQ_FN MulPlan plan_endo(const scal& k) {
+  MulPlan pl;
+  pl.first = endo_recode(endo_decompose(k), pl.S);      // s[64] = 1: the leading digit is positive
+  return pl;
+}
+// curve4q.py:437-442
+template <class SELECT> FQ_FN ptR1 loop_endo(MulPlan& pl, SELECT select) {
+  ptR1 Q = pt_r2_to_r4(select(pl.first));
   FQ_NOUNROLL
   for (int i = 63; i >= 0; i--) {
     pt_dbl(Q);
     u32 idx, neg;
-    endo_next_digit(S, idx, neg);
+    endo_next_digit(pl.S, idx, neg);
     Q = pt_add(Q, pt_r2_cneg(neg, select(idx)));
   }
   return Q;
 }
+template <class SELECT> FQ_FN ptR1 mul_endo(const scal& k, SELECT select) {
+  MulPlan pl = plan_endo(k);
+  return loop_endo(pl, select);
+}
 
-// DH_endo (curve4q.py:467-468) after validation: same shell as dh_variable_base with MUL_endo
-FQ_FN u32 dh_variable_base_endo(const scal& k, const fp2& x, const fp2& y, const TabView& T, fp2& ox, fp2& oy) {
+// DH_endo (curve4q.py:467-468) after validation: the phases of dh.cuh with table_endo / MUL_endo
+FQ_FN void dh_setup_endo(const scal& k, const fp2& x, const fp2& y, const TabView& T, DhState& D) {
   ptR1 Q = pt_clear_cofactor(x, y);
-  SelectShared sel; sel.T = T;
-  sel.T7 = endo_tab_build(T, Q);
-  ptR1 R = mul_endo(k, sel);
-  pt_to_affine(R, ox, oy);
-  bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());
-  return neutral ? FQ_ST_NEUTRAL : FQ_ST_OK;
+  D.T7 = endo_tab_build(T, Q);
+  D.plan = plan_endo(k);
+}
+FQ_FN ptR1 dh_loop_endo(const TabView& T, DhState& D) {
+  SelectShared sel; sel.T = T; sel.T7 = D.T7;
+  return loop_endo(D.plan, sel);
 }

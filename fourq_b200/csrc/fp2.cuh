@@ -59,3 +59,16 @@ FQ_FN fp2 fp2_inv(const fp2& a) {
   fpb N = fp_prep(n);
   return fp2_set(fp_mul_prep(a.re, N), fp_mul_prep(fp_neg(a.im), N));
 }
+
+// ---------------------------------------------------------------- out-of-line copies
+// The once-per-row setup code (decode, cofactor clearing, endomorphisms, table build) is long and straight-line; inlining
+// every multiplication there makes the kernel several hundred KiB of code and the instruction cache thrash.  These
+// copies are real calls (arguments and result in registers); the hot loops keep using the inlined versions.
+#ifdef FQ_HOSTSIM
+#define FQ_CALL static inline
+#else
+#define FQ_CALL static __device__ __noinline__
+#endif
+FQ_CALL fp2 fp2_mul_c(fp2 a, fp2 b) { return fp2_mul(a, b); }
+FQ_CALL fp2 fp2_sqr_c(fp2 a) { return fp2_sqr(a); }
+FQ_CALL fp fp_invsqrt_c(fp a) { return fp_invsqrt(a); }

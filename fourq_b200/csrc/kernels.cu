@@ -1,22 +1,9 @@
 // kernels.cu -- CUDA kernels for sm_100a.  One thread = one row everywhere; rows are read and written with 128-bit
 // vector accesses (a warp touches 1 KiB contiguous per operand).  The arithmetic lives in rows.cuh and below.
 #include "kernels.h"
-#include "rows.cuh"
-
-#define FQ_DH_THREADS 128
-#define FQ_DH_SMEM (56 * 16 * FQ_DH_THREADS)       // 7 table entries x 8 quads x 16 B per thread
+#include "kio.cuh"
 
 __constant__ u32 c_base_tabs[1024];                 // table_windowed(G) | table_windowed([392]G) | table_endo(G) | table_endo([392]G)
-
-__device__ __forceinline__ void ld8(const void* base, size_t row, u32* w) {
-  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * row;
-  uint4 a = p[0], b = p[1];
-  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-}
-__device__ __forceinline__ void st8(void* base, size_t row, const u32* w) {
-  uint4* p = reinterpret_cast<uint4*>(base) + 2 * row;
-  p[0] = make_uint4(w[0], w[1], w[2], w[3]); p[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
 
 template <int OP> __global__ void __launch_bounds__(256) k_fp2_op(const void* a, const void* b, void* out, size_t n) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,28 +31,6 @@ __global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_
   ld8(xy, 2 * row, wi); ld8(xy, 2 * row + 1, wi + 8);
   row_encode(wi, wo);
   st8(enc, row, wo);
-}
-
-// variable-base DH.  AFFINE = false: fq_dh (32 B encoded point in, 32 B out); true: fq_dh_affine (64 B in, 64 B out)
-template <bool AFFINE, bool ENDO> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
-k_dh(const void* k, const void* pt, void* out, unsigned char* status, size_t n) {
-  extern __shared__ uint4 smem[];
-  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
-  TabView T; T.base = smem + threadIdx.x; T.stride = blockDim.x;
-  u32 wk[8];
-  ld8(k, row, wk);
-  if (AFFINE) {
-    u32 wi[16], wo[16];
-    ld8(pt, 2 * row, wi); ld8(pt, 2 * row + 1, wi + 8);
-    status[row] = (unsigned char)row_dh_affine<ENDO>(wk, wi, wo, T);
-    st8(out, 2 * row, wo); st8(out, 2 * row + 1, wo + 8);
-  } else {
-    u32 we[8], wo[8];
-    ld8(pt, row, we);
-    status[row] = (unsigned char)row_dh<ENDO>(wk, we, wo, T);
-    st8(out, row, wo);
-  }
 }
 
 // fixed base: [k]G (DH = false) or [k][392]G with neutral rejection (DH = true); table in the constant bank
@@ -106,14 +71,11 @@ template <int V> __global__ void __launch_bounds__(256) k_imad_peak(u32* out, u3
 
 // ---------------------------------------------------------------- launch wrappers
 
-static inline unsigned grid_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 cudaError_t fqk_device_init(cudaStream_t s) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_dh<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_dh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_dh<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_dh<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM)) != cudaSuccess) return e;
+  if ((e = fqk_dh_windowed_init()) != cudaSuccess) return e;
+  if ((e = fqk_dh_endo_init()) != cudaSuccess) return e;
   u32* tabs = nullptr; uint4* scratch = nullptr;
   if ((e = cudaMalloc(&tabs, 1024 * sizeof(u32))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&scratch, 56 * sizeof(uint4))) != cudaSuccess) { cudaFree(tabs); return e; }
@@ -151,14 +113,11 @@ cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s) {
   return cudaGetLastError();
 }
 cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  unsigned g = grid_for(n, FQ_DH_THREADS);
-  unsigned char* st = (unsigned char*)status;
-  if (affine && endo) k_dh<true, true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
-  else if (affine) k_dh<true, false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
-  else if (endo) k_dh<false, true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
-  else k_dh<false, false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(k, pt, out, st, n);
-  return cudaGetLastError();
+  int dev = 0, sms = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  return endo ? fqk_dh_endo(affine, k, pt, out, status, n, sms, s) : fqk_dh_windowed(affine, k, pt, out, status, n, sms, s);
 }
 cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;

@@ -10,6 +10,11 @@ cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n
 cudaError_t fqk_decode(const void* enc, void* xy, void* status, size_t n, cudaStream_t s);
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s);
 cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s);
+// per-algorithm translation units (kernels_dh_windowed.cu, kernels_dh_endo.cu)
+cudaError_t fqk_dh_windowed_init();
+cudaError_t fqk_dh_endo_init();
+cudaError_t fqk_dh_windowed(int affine, const void* k, const void* pt, void* out, void* status, size_t n, int sms, cudaStream_t s);
+cudaError_t fqk_dh_endo(int affine, const void* k, const void* pt, void* out, void* status, size_t n, int sms, cudaStream_t s);
 cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s);
 cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s);

@@ -17,10 +17,10 @@ FQ_FN fp2 curve_gx() { return fp2_set(fp_set(0x7b3833aau, 0x286592adu, 0x7c2fb30
 FQ_FN fp2 curve_gy() { return fp2_set(fp_set(0x2bcbb287u, 0xb924a246u, 0xa120785au, 0x0e3fee9bu), fp_set(0x844c8b5cu, 0x49a7c344u, 0x630e0242u, 0x6e1c4af8u)); }
 
 // curve4q.py:23-29:  y^2 - x^2 == 1 + d x^2 y^2
-FQ_FN bool pt_on_curve(const fp2& x, const fp2& y) {
-  fp2 x2 = fp2_sqr(x), y2 = fp2_sqr(y);
+FQ_CALL bool pt_on_curve(fp2 x, fp2 y) {
+  fp2 x2 = fp2_sqr_c(x), y2 = fp2_sqr_c(y);
   fp2 lhs = fp2_sub(y2, x2);
-  fp2 rhs = fp2_add(fp2_one(), fp2_mul(fp2_mul(curve_d(), x2), y2));
+  fp2 rhs = fp2_add(fp2_one(), fp2_mul_c(fp2_mul_c(curve_d(), x2), y2));
   return fp2_eq(lhs, rhs);
 }
 
@@ -81,18 +81,27 @@ FQ_FN ptR1 pt_add_core(const ptR3p& P, const ptR2& S) {
 // curve4q.py:174-175
 FQ_FN ptR1 pt_add(const ptR1& Q, const ptR2& S) { return pt_add_core(pt_r1_to_r3p(Q), S); }
 
+// Out-of-line copies of the group law for the once-per-row setup code (see fp2.cuh); operands pass through memory.
+struct ptR3 { fp2 N, D, E, F; };        // R3 = (X+Y, Y-X, Z, T), not prepared
+FQ_CALL void pt_dbl_c(ptR1* Q) { ptR1 q = *Q; pt_dbl(q); *Q = q; }
+FQ_CALL void pt_r1_to_r3_c(ptR3* R, const ptR1* P) {                                     // curve4q.py:119-126
+  R->N = fp2_add(P->X, P->Y); R->D = fp2_sub(P->Y, P->X); R->E = P->Z; R->F = fp2_mul(P->Ta, P->Tb);
+}
+FQ_CALL void pt_add_core_c(ptR1* out, const ptR3* P, const ptR2* S) {                    // curve4q.py:155-171
+  ptR3p Pp; Pp.N = fp2_prep(P->N); Pp.D = fp2_prep(P->D); Pp.E = fp2_prep(P->E); Pp.F = fp2_prep(P->F);
+  *out = pt_add_core(Pp, *S);
+}
+FQ_CALL void pt_r1_to_r2_c(ptR2* R, const ptR1* P) { *R = pt_r1_to_r2(*P); }             // curve4q.py:109-116
+
 // curve4q.py:450-455.  [392]P = 8 * 49 P: DBL, ADD, 4 DBL, ADD, 3 DBL
 FQ_FN ptR1 pt_clear_cofactor(const fp2& x, const fp2& y) {
-  ptR1 P0 = pt_from_affine(x, y);
-  ptR2 B = pt_r1_to_r2(P0);
-  ptR1 Q = P0;
-  pt_dbl(Q);
-  Q = pt_add(Q, B);
+  ptR1 Q = pt_from_affine(x, y);
+  ptR2 B; pt_r1_to_r2_c(&B, &Q);
   FQ_NOUNROLL
-  for (int i = 0; i < 4; i++) pt_dbl(Q);
-  Q = pt_add(Q, B);
-  FQ_NOUNROLL
-  for (int i = 0; i < 3; i++) pt_dbl(Q);
+  for (int i = 0; i < 10; i++) {              // steps 1 and 6 are the additions
+    if (i == 1 || i == 6) { ptR3 Q3; pt_r1_to_r3_c(&Q3, &Q); pt_add_core_c(&Q, &Q3, &B); }
+    else pt_dbl_c(&Q);
+  }
   return Q;
 }
 

@@ -51,21 +51,40 @@ FQ_FN void row_encode(const u32* xy, u32* enc) {
 
 FQ_FN void row_zero(u32* w, int n) { for (int i = 0; i < n; i++) w[i] = 0; }
 
-// fq_dh / fq_dh_endo: decode(enc) -> DH_windowed | DH_endo -> encode
-template <bool ENDO> FQ_FN u32 row_dh(const u32* k, const u32* enc, u32* out, const TabView& T) {
-  fp2 x, y, ox, oy;
-  u32 st = pt_decode(enc, x, y);
-  if (st == FQ_ST_OK) st = ENDO ? dh_variable_base_endo(row_load_scalar(k), x, y, T, ox, oy) : dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
-  if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);
+// fq_dh / fq_dh_endo (AFFINE = false): decode(enc) -> DH_windowed | DH_endo -> encode, 8 words in, 8 out.
+// fq_dh_affine / fq_dh_endo_affine (AFFINE = true): DH_* on an affine point, 16 words in, 16 out.
+// Three phases (see dh.cuh); a row that fails validation still runs them (on a harmless value) so that every thread of
+// a CTA reaches the barriers the kernel puts between phases; its status is kept and its output zero-filled.
+template <bool ENDO, bool AFFINE> FQ_FN u32 row_dh_setup(const u32* k, const u32* pt, const TabView& T, DhState& D) {
+  fp2 x, y;
+  u32 st;
+  if (AFFINE) {
+    x = fp2_canon(row_load_fp2(pt)); y = fp2_canon(row_load_fp2(pt + 8));
+    st = pt_on_curve(x, y) ? FQ_ST_OK : FQ_ST_NOT_ON_CURVE;                         // curve4q.py:447
+  } else {
+    st = pt_decode(pt, x, y);
+  }
+  if (ENDO) dh_setup_endo(row_load_scalar(k), x, y, T, D); else dh_setup_windowed(row_load_scalar(k), x, y, T, D);
   return st;
 }
-// fq_dh_affine / fq_dh_endo_affine: DH_windowed | DH_endo on an affine point (64 B in, 64 B out)
-template <bool ENDO> FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* out, const TabView& T) {
-  fp2 x = fp2_canon(row_load_fp2(xy)), y = fp2_canon(row_load_fp2(xy + 8)), ox, oy;
-  u32 st = pt_on_curve(x, y) ? FQ_ST_OK : FQ_ST_NOT_ON_CURVE;                       // curve4q.py:447
-  if (st == FQ_ST_OK) st = ENDO ? dh_variable_base_endo(row_load_scalar(k), x, y, T, ox, oy) : dh_variable_base(row_load_scalar(k), x, y, T, ox, oy);
-  if (st == FQ_ST_OK) { row_store_fp2(out, ox); row_store_fp2(out + 8, oy); } else row_zero(out, 16);
+template <bool ENDO> FQ_FN ptR1 row_dh_loop(const TabView& T, DhState& D) { return ENDO ? dh_loop_endo(T, D) : dh_loop_windowed(T, D); }
+template <bool AFFINE> FQ_FN u32 row_dh_finish(u32 st, const ptR1& R, u32* out) {
+  fp2 ox, oy;
+  u32 st2 = dh_finish(R, ox, oy);
+  if (st == FQ_ST_OK) st = st2;
+  if (AFFINE) { if (st == FQ_ST_OK) { row_store_fp2(out, ox); row_store_fp2(out + 8, oy); } else row_zero(out, 16); }
+  else { if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8); }
   return st;
+}
+template <bool ENDO> FQ_FN u32 row_dh(const u32* k, const u32* enc, u32* out, const TabView& T) {
+  DhState D;
+  u32 st = row_dh_setup<ENDO, false>(k, enc, T, D);
+  return row_dh_finish<false>(st, row_dh_loop<ENDO>(T, D), out);
+}
+template <bool ENDO> FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* out, const TabView& T) {
+  DhState D;
+  u32 st = row_dh_setup<ENDO, true>(k, xy, T, D);
+  return row_dh_finish<true>(st, row_dh_loop<ENDO>(T, D), out);
 }
 // fq_mul_base (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base (true): encode([k][392]G) with the neutral check
 template <bool CHECK_NEUTRAL, bool ENDO> FQ_FN u32 row_fixed_base(const u32* k, const u32* tab, u32* out) {
