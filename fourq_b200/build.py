@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfourq_b200.so")
-SOURCES = ["kernels.cu", "kernels_dh_windowed.cu", "kernels_dh_endo.cu", "x25519.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "kernels_dh_windowed.cu", "kernels_dh_endo.cu", "kernels_comb.cu", "x25519.cu", "capi.cu"]
 NVCC_FLAGS = os.environ.get("FQ_NVCC_EXTRA", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-cudart", "static"]
 

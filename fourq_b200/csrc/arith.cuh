@@ -27,6 +27,16 @@ namespace fqsim { extern thread_local u32 cc; }
 #define FQ_NOUNROLL _Pragma("unroll 1")
 #endif
 
+// Scheduling fence.  ptxas interleaves every independent carry chain it can find; with several multiplications in one
+// basic block it keeps more than the 7 predicate registers' worth of carries in flight and spills them into general
+// registers (P2R / bit set / bit test: ~11 % of the instructions of a point addition).  A warp-level sync is one cheap
+// instruction that ends the scheduling region, so chains of different multiplications no longer overlap.
+#if defined(FQ_HOSTSIM) || !defined(FQ_USE_FENCE)
+#define FQ_SCHED_FENCE() do {} while (0)
+#else
+#define FQ_SCHED_FENCE() __syncwarp()
+#endif
+
 // ---------------------------------------------------------------- add / sub with carry
 FQ_FN u32 add_cc(u32 a, u32 b) {
 #ifdef FQ_HOSTSIM

@@ -39,6 +39,8 @@ struct DevCtx {
   cudaStream_t st[kStreams];
   Slot slot[kStreams];
   void* flush = nullptr;
+  void* comb = nullptr;       // per-digit fixed-base tables (kernels_comb.cu)
+  int sms = 0;
 };
 DevCtx g_ctx[kMaxDev];
 
@@ -55,6 +57,8 @@ int ctx_init(int dev) {
   if (c.ready) return FQ_OK;
   for (int i = 0; i < kStreams; i++) CU(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
   CU(fqk_device_init(c.st[0]));
+  CU(fqk_comb_init(&c.comb, c.st[0]));
+  CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
   c.ready = true;
   return FQ_OK;
 }
@@ -82,13 +86,17 @@ OpDesc describe(int op) {
     case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, (size_t)1 << 17};
     case FQ_DEVOP_DH_BASE: case FQ_DEVOP_DH_ENDO_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
     case FQ_DEVOP_MUL_BASE: case FQ_DEVOP_MUL_ENDO_BASE: return {op, 32, 0, 32, false, (size_t)1 << 17};
+    case FQ_DEVOP_DH_BASE_COMB: return {op, 32, 0, 32, true, (size_t)1 << 18};
+    case FQ_DEVOP_MUL_BASE_COMB: return {op, 32, 0, 32, false, (size_t)1 << 18};
     case FQ_DEVOP_X25519: return {op, 32, 32, 32, false, (size_t)1 << 17};
     default: return {-1, 0, 0, 0, false, 0};
   }
 }
 
-cudaError_t launch(int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s) {
+cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s) {
   switch (op) {
+    case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, cx.comb, a, out, status, n, cx.sms, s);
+    case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, cx.comb, a, out, nullptr, n, cx.sms, s);
     case FQ_DEVOP_FP2_MUL: return fqk_fp2_op(FQK_MUL, a, b, out, n, s);
     case FQ_DEVOP_FP2_SQR: return fqk_fp2_op(FQK_SQR, a, b, out, n, s);
     case FQ_DEVOP_FP2_INV: return fqk_fp2_op(FQK_INV, a, b, out, n, s);
@@ -149,7 +157,7 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* 
       ChunkEv ev; ev.dev = i;
       CU(cudaEventCreate(&ev.e0)); CU(cudaEventCreate(&ev.e1));
       CU(cudaEventRecord(ev.e0, st));
-      CU(launch(op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st));
+      CU(launch(cx, op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st));
       CU(cudaEventRecord(ev.e1, st));
       evs.push_back(ev);
       CU(cudaMemcpyAsync(out + r0 * d.out_bytes, s.buf[2], rows * d.out_bytes, cudaMemcpyDeviceToHost, st));
@@ -212,6 +220,8 @@ int fq_dh_endo(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_
 int fq_dh_endo_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_AFFINE, k, xy, xy_out, status, n, ndev); }
 int fq_dh_endo_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_BASE, k, nullptr, enc_out, status, n, ndev); }
 int fq_mul_endo_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_ENDO_BASE, k, nullptr, enc_out, nullptr, n, ndev); }
+int fq_dh_base_comb(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_BASE_COMB, k, nullptr, enc_out, status, n, ndev); }
+int fq_mul_base_comb(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_BASE_COMB, k, nullptr, enc_out, nullptr, n, ndev); }
 int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_X25519, k, u, out, nullptr, n, ndev); }
 
 int fq_host_alloc(void** p, size_t bytes) {
@@ -262,7 +272,7 @@ int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* s
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, st));
-  for (int i = 0; i < iters; i++) CU(launch(op, a, b, out, status, n, st));
+  for (int i = 0; i < iters; i++) CU(launch(g_ctx[dev], op, a, b, out, status, n, st));
   CU(cudaEventRecord(e1, st));
   CU(cudaEventSynchronize(e1));
   float t = 0.f;

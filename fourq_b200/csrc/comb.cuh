@@ -1,0 +1,118 @@
+// comb.cuh -- fixed-base scalar multiplication with one precomputed table per digit.
+//
+// The reference's fixed-base entry points are MUL_*(m, G, table=T) = [m]G (curve4q.py:582-584) and
+// DH_*(m, G, table=T392) = [392 m]G (curve4q.py:743-762); the draft points to "FourQlib's fixed-base algorithm" for key
+// generation (draft-ladd-cfrg-4q.md:702-705, :727-729).  The affine result is canonical, so any correct algorithm gives
+// the reference's bytes.  Here the base point B is fixed, so all doublings are precomputed:
+//
+//     r = m mod N (+N if even) = sum_{i=0}^{62} d_i 16^i,  d_i odd in [-15, 15], d_62 = 1      (scalar.cuh, curve4q.py:216-226)
+//     [r]B = [16^62]B + sum_{i=0}^{61} sign(d_i) * T_i[(|d_i|-1)/2],      T_i[j] = [(2j+1) 16^i]B
+//
+// 62 mixed additions (7 GF(p^2) multiplications each, the table entries have Z = 1) and no doubling: 20,832 32x32->64
+// multiply-adds per row instead of 92,624 for MUL_windowed with a table.  T_i[j] is stored as
+// (x+y, y-x, 2dxy) = 96 B; a base needs 63 x 8 x 96 B = 47.25 KiB, which a CTA copies from global to shared memory.
+// The scan over the 8 entries of T_i reads the SAME addresses in every thread (broadcast LDS) and keeps one entry with
+// masks: no secret-dependent address or branch.
+#pragma once
+#include "dh.cuh"
+
+struct ptA3 { fp2 N, D, F; };                        // affine point as (x+y, y-x, 2dxy)
+
+#define FQ_COMB_DIGITS 63
+#define FQ_COMB_ENTRY_WORDS 24                       // N.re N.im D.re D.im F.re F.im, 4 words each
+#define FQ_COMB_DIGIT_WORDS (8 * FQ_COMB_ENTRY_WORDS)
+#define FQ_COMB_WORDS (FQ_COMB_DIGITS * FQ_COMB_DIGIT_WORDS)      // 12,096 words = 48,384 B per base point
+
+// R1 + (affine, Z = 1) -> R1: ADD_core (curve4q.py:155-171) with E2 = 2 Z2 = 2, so D = Z1 * E2 is a doubling.
+FQ_FN ptR1 pt_madd(const ptR1& Q, const ptA3& S) {
+  fp2b N1 = fp2_prep(fp2_add(Q.X, Q.Y)), D1 = fp2_prep(fp2_sub(Q.Y, Q.X)), T1 = fp2_prep(fp2_mul(Q.Ta, Q.Tb));
+  fp2 A = fp2_mul_prep(S.D, D1), B = fp2_mul_prep(S.N, N1), C = fp2_mul_prep(S.F, T1), D = fp2_dbl(Q.Z);
+  fp2 E = fp2_sub(B, A), F = fp2_sub(D, C), G = fp2_add(D, C), H = fp2_add(B, A);
+  fp2b Fp = fp2_prep(F), Gp = fp2_prep(G);
+  ptR1 R;
+  R.X = fp2_mul_prep(E, Fp); R.Y = fp2_mul_prep(H, Gp); R.Z = fp2_mul_prep(G, Fp); R.Ta = E; R.Tb = H;
+  return R;
+}
+
+FQ_FN ptA3 a3_load(const u32* w) {
+  ptA3 P;
+  P.N = fp2_set(fp_set(w[0], w[1], w[2], w[3]), fp_set(w[4], w[5], w[6], w[7]));
+  P.D = fp2_set(fp_set(w[8], w[9], w[10], w[11]), fp_set(w[12], w[13], w[14], w[15]));
+  P.F = fp2_set(fp_set(w[16], w[17], w[18], w[19]), fp_set(w[20], w[21], w[22], w[23]));
+  return P;
+}
+
+// constant-time T_i[idx] with the sign applied (curve4q.py:193-195: -(N, D, F) = (D, N, -F)); tab = the 192 words of T_i
+FQ_FN ptA3 comb_select(const u32* tab, u32 idx, u32 neg) {
+  u32 w[FQ_COMB_ENTRY_WORDS];
+  FQ_UNROLL
+  for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] = 0;
+  FQ_UNROLL
+  for (int e = 0; e < 8; e++) {
+    u32 m = (idx == (u32)e) ? 0xffffffffu : 0u;
+    FQ_UNROLL
+    for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] |= tab[e * FQ_COMB_ENTRY_WORDS + j] & m;
+  }
+  ptA3 P = a3_load(w), R;
+  R.N = fp2_select(neg, P.D, P.N); R.D = fp2_select(neg, P.N, P.D);
+  R.F.re = fp_set(P.F.re.v[0] ^ neg, P.F.re.v[1] ^ neg, P.F.re.v[2] ^ neg, P.F.re.v[3] ^ (neg & FQ_P3));
+  R.F.im = fp_set(P.F.im.v[0] ^ neg, P.F.im.v[1] ^ neg, P.F.im.v[2] ^ neg, P.F.im.v[3] ^ (neg & FQ_P3));
+  return R;
+}
+
+// [k]B for the base point whose tables are `tab` (FQ_COMB_WORDS words); returns R1
+FQ_FN ptR1 mul_comb(const scal& k, const u32* tab) {
+  MulPlan pl = plan_windowed(k);
+  // leading digit d_62 = +1: start from T_62[0] = [16^62]B, back in (x, y) from (x+y, y-x)
+  ptA3 S = a3_load(tab + 62 * FQ_COMB_DIGIT_WORDS);
+  fp2 x = fp2_set(fp_half(fp_sub(S.N.re, S.D.re)), fp_half(fp_sub(S.N.im, S.D.im)));
+  fp2 y = fp2_set(fp_half(fp_add(S.N.re, S.D.re)), fp_half(fp_add(S.N.im, S.D.im)));
+  ptR1 Q = pt_from_affine(x, y);
+  FQ_NOUNROLL
+  for (int i = 61; i >= 0; i--) {
+    u32 idx, neg;
+    scal_next_digit(pl.S, idx, neg);
+    Q = pt_madd(Q, comb_select(tab + i * FQ_COMB_DIGIT_WORDS, idx, neg));
+  }
+  return Q;
+}
+
+// fq_mul_base_comb (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base_comb (true): encode([k][392]G), neutral rejected
+template <bool CHECK_NEUTRAL> FQ_FN u32 row_comb(const u32* k, const u32* tab, u32* out) {
+  scal s;
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) s.v[i] = k[i];
+  fp2 ox, oy;
+  pt_to_affine(mul_comb(s, tab), ox, oy);
+  u32 st = FQ_ST_OK;
+  if (CHECK_NEUTRAL && (fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one()))) st = FQ_ST_NEUTRAL;   // curve4q.py:459
+  if (st == FQ_ST_OK) pt_encode(ox, oy, out);
+  else { FQ_UNROLL for (int i = 0; i < 8; i++) out[i] = 0; }
+  return st;
+}
+
+// Table construction, one call per (base, digit): out = the 192 words of T_i for B = G (which = 0) or [392]G (which = 1).
+// P = [16^i]B by 4 i doublings, then the odd multiples as in table_windowed (curve4q.py:179-185), each normalised to
+// affine.  Run once per device at context creation (126 threads); also by the CPU simulation in tests/hostsim.
+FQ_FN void comb_build_digit(int which, int i, u32* out) {
+  ptR1 P = (which == 0) ? pt_from_affine(curve_gx(), curve_gy()) : pt_clear_cofactor(curve_gx(), curve_gy());
+  FQ_NOUNROLL
+  for (int t = 0; t < 4 * i; t++) pt_dbl_c(&P);
+  ptR1 P2 = P;
+  pt_dbl_c(&P2);
+  ptR3 P23; pt_r1_to_r3_c(&P23, &P2);
+  ptR1 M = P;
+  FQ_NOUNROLL
+  for (int j = 0; j < 8; j++) {
+    fp2 x, y;
+    pt_to_affine(M, x, y);
+    fp2 N = fp2_canon(fp2_add(x, y)), D = fp2_canon(fp2_sub(y, x));
+    fp2 F = fp2_canon(fp2_mul_c(fp2_mul_c(x, y), curve_2d()));
+    u32* w = out + j * FQ_COMB_ENTRY_WORDS;
+    FQ_UNROLL
+    for (int l = 0; l < 4; l++) {
+      w[l] = N.re.v[l]; w[4 + l] = N.im.v[l]; w[8 + l] = D.re.v[l]; w[12 + l] = D.im.v[l]; w[16 + l] = F.re.v[l]; w[20 + l] = F.im.v[l];
+    }
+    if (j < 7) { ptR2 Mr2; pt_r1_to_r2_c(&Mr2, &M); pt_add_core_c(&M, &P23, &Mr2); }     // M += 2P
+  }
+}

@@ -24,6 +24,24 @@ FQ_FN bool fp2_eq_canon(const fp2& a, const fp2& b) { return fp_eq_canon(a.re, b
 FQ_FN bool fp2_eq(const fp2& a, const fp2& b) { return fp2_eq_canon(fp2_canon(a), fp2_canon(b)); }
 FQ_FN fp2 fp2_select(u32 m, const fp2& x, const fp2& y) { return fp2_set(fp_select(m, x.re, y.re), fp_select(m, x.im, y.im)); }  // fields.py:237
 
+#ifdef FQ_FP2_SCHOOLBOOK
+// Variant: four GF(p) products in two accumulators, (a0 b0 + (p - a1) b1, a0 b1 + a1 b0): 64 IMAD.WIDE but no
+// combination step (no merges of partial products, no multiword subtractions) and no prepared sum.  a must be tight.
+FQ_FN fp2b fp2_prep(const fp2& b) {
+  fp2b B;
+  B.re = fp_prep(b.re); B.im = fp_prep(b.im); B.sum = B.re;
+  return B;
+}
+FQ_FN fp2 fp2_mul_prep(const fp2& a, const fp2b& B) {
+  facc A0, A1;
+  facc_mul<true>(A0, a.re, B.re); facc_mul<false>(A0, fp_neg(a.im), B.im);
+  facc_mul<true>(A1, a.re, B.im); facc_mul<false>(A1, a.im, B.re);
+  fp2 r;
+  r.re = fp_fold(facc_merge(A0));
+  r.im = fp_fold(facc_merge(A1));
+  return r;
+}
+#else
 FQ_FN fp2b fp2_prep(const fp2& b) {
   fp2b B;
   B.re = fp_prep(b.re); B.im = fp_prep(b.im); B.sum = fp_prep(fp_add(b.re, b.im));
@@ -43,6 +61,7 @@ FQ_FN fp2 fp2_mul_prep(const fp2& a, const fp2b& B) {
   r.im = fp_fold(fpw_sub(fpw_sub(t2, t0), t1));
   return r;
 }
+#endif
 FQ_FN fp2 fp2_mul(const fp2& a, const fp2& b) { return fp2_mul_prep(a, fp2_prep(b)); }
 
 // fields.py:176-181.  ((a0+a1)(a0-a1), 2 a0 a1)

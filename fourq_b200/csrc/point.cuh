@@ -57,25 +57,33 @@ FQ_FN ptR2 pt_r2_cneg(u32 m, const ptR2& P) {
 
 // curve4q.py:138-152.  R1/R4 -> R1, 4 S + 3 M (the reference's multiplication by the constant 2 is a rotation here)
 FQ_FN void pt_dbl(ptR1& Q) {
-  fp2 A = fp2_sqr(Q.X), B = fp2_sqr(Q.Y);
-  fp2 C = fp2_dbl(fp2_sqr(Q.Z));
+  fp2 A = fp2_sqr(Q.X); FQ_SCHED_FENCE();
+  fp2 B = fp2_sqr(Q.Y); FQ_SCHED_FENCE();
+  fp2 C = fp2_dbl(fp2_sqr(Q.Z)); FQ_SCHED_FENCE();
   fp2 D = fp2_add(A, B);
-  fp2 E = fp2_sub(fp2_sqr(fp2_add(Q.X, Q.Y)), D);
+  fp2 E = fp2_sub(fp2_sqr(fp2_add(Q.X, Q.Y)), D); FQ_SCHED_FENCE();
   fp2 F = fp2_sub(B, A);
   fp2 G = fp2_sub(C, F);
   fp2b Gp = fp2_prep(G), Fp = fp2_prep(F);
-  Q.X = fp2_mul_prep(E, Gp); Q.Y = fp2_mul_prep(D, Fp); Q.Z = fp2_mul_prep(F, Gp);
+  Q.X = fp2_mul_prep(E, Gp); FQ_SCHED_FENCE();
+  Q.Y = fp2_mul_prep(D, Fp); FQ_SCHED_FENCE();
+  Q.Z = fp2_mul_prep(F, Gp); FQ_SCHED_FENCE();
   Q.Ta = E; Q.Tb = D;
 }
 
 // curve4q.py:155-171.  R3 (prepared) + R2 -> R1, 7 M
 FQ_FN ptR1 pt_add_core(const ptR3p& P, const ptR2& S) {
-  fp2 A = fp2_mul_prep(S.D, P.D), B = fp2_mul_prep(S.N, P.N);
-  fp2 C = fp2_mul_prep(S.F, P.F), D = fp2_mul_prep(S.E, P.E);
+  fp2 A = fp2_mul_prep(S.D, P.D); FQ_SCHED_FENCE();
+  fp2 B = fp2_mul_prep(S.N, P.N); FQ_SCHED_FENCE();
+  fp2 C = fp2_mul_prep(S.F, P.F); FQ_SCHED_FENCE();
+  fp2 D = fp2_mul_prep(S.E, P.E); FQ_SCHED_FENCE();
   fp2 E = fp2_sub(B, A), F = fp2_sub(D, C), G = fp2_add(D, C), H = fp2_add(B, A);
   fp2b Fp = fp2_prep(F), Gp = fp2_prep(G);
   ptR1 R;
-  R.X = fp2_mul_prep(E, Fp); R.Y = fp2_mul_prep(H, Gp); R.Z = fp2_mul_prep(G, Fp); R.Ta = E; R.Tb = H;
+  R.X = fp2_mul_prep(E, Fp); FQ_SCHED_FENCE();
+  R.Y = fp2_mul_prep(H, Gp); FQ_SCHED_FENCE();
+  R.Z = fp2_mul_prep(G, Fp); FQ_SCHED_FENCE();
+  R.Ta = E; R.Tb = H;
   return R;
 }
 // curve4q.py:174-175

@@ -11,7 +11,9 @@
 
 algorithm = "windowed" runs MUL_windowed (curve4q.py:188-235), "endo" runs MUL_endo (curve4q.py:405-442); the results
 are bit-identical (the reference asserts it, curve4q.py:706-762), "endo" needs about 1.8x fewer field multiplications
-and is the default.
+and is the default.  The fixed-base entry points DH_base / MUL_base also take algorithm = "comb" (their default): one
+precomputed table per digit, 62 mixed additions and no doubling -- the fixed-base method the draft recommends for key
+generation (draft-ladd-cfrg-4q.md:702-705, :727-729); same bytes again because the affine result is canonical.
 
 Scalars are 32-byte little-endian unsigned rows (no clamping).  Exceptions of the reference become per-row status codes;
 failed rows are zero-filled.  `strict=True` raises the reference's message for the first failing row instead.
@@ -25,10 +27,14 @@ DEFAULT_ALGORITHM = "endo"
 _ALGS = ("windowed", "endo")
 
 
-def _alg(algorithm):
-    a = DEFAULT_ALGORITHM if algorithm is None else algorithm
-    if a not in _ALGS:
-        raise ValueError("algorithm must be one of %r" % (_ALGS,))
+DEFAULT_BASE_ALGORITHM = "comb"
+_BASE_ALGS = ("windowed", "endo", "comb")
+
+
+def _alg(algorithm, base=False):
+    a = (DEFAULT_BASE_ALGORITHM if base else DEFAULT_ALGORITHM) if algorithm is None else algorithm
+    if a not in (_BASE_ALGS if base else _ALGS):
+        raise ValueError("algorithm must be one of %r" % ((_BASE_ALGS if base else _ALGS),))
     return a
 
 
@@ -123,7 +129,7 @@ def DH_base(k, ndev=1, strict=False, out=None, status=None, algorithm=None):
     n = k.shape[0]
     out = _buf(out, (n, 32), "out")
     status = _buf(status, (n,), "status")
-    fn = _lib.lib().fq_dh_endo_base if _alg(algorithm) == "endo" else _lib.lib().fq_dh_base
+    fn = getattr(_lib.lib(), {"windowed": "fq_dh_base", "endo": "fq_dh_endo_base", "comb": "fq_dh_base_comb"}[_alg(algorithm, base=True)])
     _lib.check(fn(_lib.ptr(k), _lib.ptr(out), _lib.ptr(status), n, ndev))
     if strict:
         _raise_first(status)
@@ -133,7 +139,7 @@ def DH_base(k, ndev=1, strict=False, out=None, status=None, algorithm=None):
 def MUL_base(k, ndev=1, out=None, algorithm=None):
     k = _lib.rows(k, 32, "k")
     out = _buf(out, (k.shape[0], 32), "out")
-    fn = _lib.lib().fq_mul_endo_base if _alg(algorithm) == "endo" else _lib.lib().fq_mul_base
+    fn = getattr(_lib.lib(), {"windowed": "fq_mul_base", "endo": "fq_mul_endo_base", "comb": "fq_mul_base_comb"}[_alg(algorithm, base=True)])
     _lib.check(fn(_lib.ptr(k), _lib.ptr(out), k.shape[0], ndev))
     return out
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 100
+#define FQ_VERSION 101
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -89,6 +89,13 @@ FQ_API int fq_dh_endo_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_ou
 FQ_API int fq_dh_endo_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev);
 FQ_API int fq_mul_endo_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev);
 
+/* Fixed base with one precomputed table per digit ("comb"): the same results as fq_mul_base / fq_dh_base (the affine
+ * point is canonical, curve4q.py:582-598 and :743-762 assert table == no table), computed as 62 mixed additions and no
+ * doubling.  This is the fixed-base algorithm the draft recommends for key generation (draft-ladd-cfrg-4q.md:702-705,
+ * :727-729: "FourQlib's fixed-base algorithm"); tables of G and [392]G are built on the device at context creation. */
+FQ_API int fq_mul_base_comb(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev);
+FQ_API int fq_dh_base_comb(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev);
+
 /* ---- X25519 (RFC 7748): impl/curve25519.py:88-91 x25519(k, u) -> 32 bytes; k, u, out are (n,32) */
 FQ_API int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev);
 
@@ -117,6 +124,8 @@ FQ_API int fq_host_free(void* p);
 #define FQ_DEVOP_DH_ENDO_AFFINE 24
 #define FQ_DEVOP_DH_ENDO_BASE 25
 #define FQ_DEVOP_MUL_ENDO_BASE 26
+#define FQ_DEVOP_DH_BASE_COMB 27    /* a = k, out, status */
+#define FQ_DEVOP_MUL_BASE_COMB 28   /* a = k, out */
 FQ_API int fq_dev_alloc(int dev, void** p, size_t bytes);
 FQ_API int fq_dev_free(int dev, void* p);
 FQ_API int fq_dev_upload(int dev, void* dst, const void* src, size_t bytes);

@@ -8,6 +8,7 @@
 #include "../../fourq_b200/csrc/rows.cuh"
 #include "../../fourq_b200/csrc/x25519.cuh"
 #include "../../fourq_b200/csrc/endo.cuh"
+#include "../../fourq_b200/csrc/comb.cuh"
 
 namespace fqsim { thread_local u32 cc = 0; }
 
@@ -92,6 +93,23 @@ int sim_fixed_base(int dh, const uint8_t* k, uint8_t* out, uint8_t* status, size
     u32 wk[8], wo[8]; memcpy(wk, k + 32 * i, 32);
     u32 st = endo ? (dh ? row_fixed_base<true, true>(wk, g_tabs + 768, wo) : row_fixed_base<false, true>(wk, g_tabs + 512, wo))
                   : (dh ? row_fixed_base<true, false>(wk, g_tabs + 256, wo) : row_fixed_base<false, false>(wk, g_tabs, wo));
+    if (status) status[i] = (uint8_t)st;
+    memcpy(out + 32 * i, wo, 32);
+  }
+  return 0;
+}
+// per-digit fixed-base tables (comb.cuh): dh = 0 -> [k]G, 1 -> [392 k]G with the neutral check
+static u32 g_comb[2 * FQ_COMB_WORDS];
+static bool g_comb_ready = false;
+int sim_comb(int dh, const uint8_t* k, uint8_t* out, uint8_t* status, size_t n) {
+  if (!g_comb_ready) {
+    for (int which = 0; which < 2; which++)
+      for (int i = 0; i < FQ_COMB_DIGITS; i++) comb_build_digit(which, i, g_comb + which * FQ_COMB_WORDS + i * FQ_COMB_DIGIT_WORDS);
+    g_comb_ready = true;
+  }
+  for (size_t i = 0; i < n; i++) {
+    u32 wk[8], wo[8]; memcpy(wk, k + 32 * i, 32);
+    u32 st = dh ? row_comb<true>(wk, g_comb + FQ_COMB_WORDS, wo) : row_comb<false>(wk, g_comb, wo);
     if (status) status[i] = (uint8_t)st;
     memcpy(out + 32 * i, wo, 32);
   }

@@ -71,6 +71,15 @@ def test_scalar_mult_golden(fq, golden, alg):
     assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh_affine"]]
 
 
+def test_fixed_base_comb_golden(fq, golden):
+    """Per-digit tables: same bytes as MUL_*(m, G, table) / DH_*(m, G, table=T392), incl. edge scalars."""
+    m = golden["mul"]
+    assert hexrows(fq.MUL_base(R([H(r[0]) for r in m["mul_base"]]), algorithm="comb")) == [r[1] for r in m["mul_base"]]
+    out, st = fq.DH_base(R([H(r[0]) for r in m["dh_base"]]), algorithm="comb")
+    assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[1], r[2]) for r in m["dh_base"]]
+    assert 5 in set(int(s) for s in st)                       # scalars = 0 mod N are rejected as in curve4q.py:459
+
+
 def test_reference_mulP_chain(fq, golden):
     """curve4q.py:549-567: 1000 chained MUL_windowed from G end at mulP, i.e. [prod c_i mod N]G == mulP."""
     m = golden["mul"]
@@ -78,7 +87,7 @@ def test_reference_mulP_chain(fq, golden):
     for k in m["mulP_chain_scalars"]:
         prod = prod * int.from_bytes(H(k), "little") % O.N
     P = O.xy_from_bytes(H(m["mulP_affine"]))
-    for alg in ("windowed", "endo"):
+    for alg in ("windowed", "endo", "comb"):
         got = fq.MUL_base(fq.curve4q.pack_scalars([prod]), algorithm=alg)
         assert bytes(got[0]) == O.encode(P[0], P[1])
     # [2^1000]G and the addition KAT (curve4q.py:516-547), via scalars
@@ -181,6 +190,9 @@ def test_full_size_properties_2_20(fq):
     AB2, _ = fq.DH(a, Bp, algorithm="endo")                              # windowed == endo on 2^20 rows (curve4q.py:706-762)
     assert (AB2 == AB).all()
     assert (fq.MUL_base(a, algorithm="windowed") == fq.MUL_base(a, algorithm="endo")).all()
+    assert (fq.MUL_base(a, algorithm="comb") == fq.MUL_base(a, algorithm="endo")).all()     # per-digit tables, 2^20 rows
+    Ac, sc = fq.DH_base(a, algorithm="comb")
+    assert not sc.any() and (Ac == A).all()
     # fixed base == variable base on G (curve4q.py:743-762)
     Genc = np.tile(np.frombuffer(O.encode(O.GX, O.GY), np.uint8), (n, 1))
     viaG, s3 = fq.DH(a, Genc)

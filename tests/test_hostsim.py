@@ -149,6 +149,19 @@ def test_fixed_base_endo_golden(sim, golden):
         assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), kk
 
 
+def test_fixed_base_comb_golden(sim, golden):
+    """Per-digit tables (comb.cuh) give the reference's bytes for MUL_*(m, G, table) and DH_*(m, G, table=T392)."""
+    rows = golden["mul"]["mul_base"]
+    k = _rows([H(r[0]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8)
+    sim.sim_comb(0, _p(k), _p(out), None, ctypes.c_size_t(len(rows)))
+    assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[1] for r in rows]
+    rows = golden["mul"]["dh_base"]
+    k = _rows([H(r[0]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8); st = np.zeros(len(rows), np.uint8)
+    sim.sim_comb(1, _p(k), _p(out), _p(st), ctypes.c_size_t(len(rows)))
+    for i, (kk, want_st, want) in enumerate(rows):
+        assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), kk
+
+
 def test_dh_golden(sim, golden):
     rows = golden["mul"]["dh"]
     k = _rows([H(r[0]) for r in rows]); e = _rows([H(r[1]) for r in rows]); n = len(rows)

@@ -67,10 +67,6 @@ int main() {
   void *k, *out; cudaMalloc(&k, n * 32); cudaMalloc(&out, n * 32);
   cudaMemset(k, 0x5a, n * 32);
   run<2, 7>("minb2 7slots", k, out, n);
-  run<2, 4>("minb2 4slots", k, out, n);
   run<3, 4>("minb3 4slots", k, out, n);
-  run<4, 3>("minb4 3slots", k, out, n);
-  run<3, 2>("minb3 2slots", k, out, n);
-  run<4, 2>("minb4 2slots", k, out, n);
   return 0;
 }
