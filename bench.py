@@ -102,14 +102,15 @@ class ClockSampler:
 
 def _cpu_row(args):
     from oracle import fourq_oracle as O
-    return O.row_dh(args[0], args[1])
+    return O.row_dh(args[0], args[1], mul=O.mul_endo if args[2] == "endo" else O.mul_windowed)
 
 
-def cpu_dh(k, pub, procs):
+def cpu_dh(k, pub, procs, algorithm):
+    """decode -> DH_windowed | DH_endo -> encode (the same reference algorithm as the GPU arm) on `procs` host processes."""
     import multiprocessing as mp
     with mp.get_context("fork").Pool(procs) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_row, [(bytes(k[i]), bytes(pub[i])) for i in range(len(k))], chunksize=max(1, len(k) // (procs * 8)))
+        res = pool.map(_cpu_row, [(bytes(k[i]), bytes(pub[i]), algorithm) for i in range(len(k))], chunksize=max(1, len(k) // (procs * 8)))
         dt = time.perf_counter() - t0
     return res, dt
 
@@ -127,18 +128,18 @@ def run_reference(args, rank):
     base = [O.row_mul_base(bytes(r)) for r in np.random.default_rng(4).integers(0, 256, (16, 32), np.uint8)]
     pub = np.frombuffer(b"".join(base[i % 16] for i in range(sample)), np.uint8).reshape(sample, 32)
     for _ in range(args.warmup):
-        cpu_dh(k[: 8 * cores], pub[: 8 * cores], cores)
+        cpu_dh(k[: 8 * cores], pub[: 8 * cores], cores, args.algorithm)
     total = 0.0
     for _ in range(args.steps):
-        _, dt = cpu_dh(k, pub, cores)
+        _, dt = cpu_dh(k, pub, cores, args.algorithm)
         total += dt
     value = sample * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_rows_per_step": sample},
+            "config": {"workload": WORKLOAD, "algorithm": "DH_%s" % args.algorithm, "sample_rows_per_step": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d rows per step x %d steps, oracle/fourq_oracle.py row_dh under multiprocessing" % (sample, args.steps)},
+                             "sample": "%d rows per step x %d steps, oracle/fourq_oracle.py row_dh (DH_%s) under multiprocessing" % (sample, args.steps, args.algorithm)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -242,8 +243,15 @@ def main():
         except OSError:
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
+        traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_dh_%s_2p20_rows_bytes" % args.algorithm)
+            if traffic is not None and rows != ROWS_PER_GPU:
+                traffic = None
+        except (OSError, ValueError):
+            pass
         roofline = {"bound": "imad", "achieved": achieved / 1e12, "peak": wide_peak / 1e12, "unit": "T IMAD.WIDE/s", "frac": achieved / wide_peak,
-                    "traffic": None,
+                    "traffic": traffic,
                     "note": "per GPU; achieved = rows/s x %d algorithmic 32x32->64 multiply-adds per row (SURVEY 8d); peak = IMAD.WIDE.U32 "
                             "issue rate measured live by fq_imad_peak (32-bit IMAD measured %.2f T/s); HBM is not the bound: "
                             "%d B/row -> %.4f of %s %.1f GB/s" % (imads, imad_peak / 1e12, BYTES_PER_ROW,
@@ -254,12 +262,12 @@ def main():
         cpu = None
         if sample > 0:
             sample = min(sample, rows)
-            res, dt = cpu_dh(k[:sample], pub[:sample], cores)
+            res, dt = cpu_dh(k[:sample], pub[:sample], cores, args.algorithm)
             got = [(bytes(out_dev[i]), int(st_dev[i])) for i in range(sample)]
             if got != res:
                 raise SystemExit("PARITY FAILURE: GPU output differs from the oracle on the CPU-baseline sample")
             cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "first %d rows of rank 0's batch, oracle row_dh under multiprocessing (%d procs); bit-exact with the GPU rows" % (sample, cores)}
+                   "sample": "first %d rows of rank 0's batch, oracle row_dh (DH_%s) under multiprocessing (%d procs); bit-exact with the GPU rows" % (sample, args.algorithm, cores)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",
