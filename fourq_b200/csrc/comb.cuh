@@ -12,7 +12,7 @@
 // multiply-adds per row instead of 92,624 for MUL_windowed with a table.  T_i[j] is stored as
 // (x+y, y-x, 2dxy) = 96 B; a base needs 63 x 8 x 96 B = 47.25 KiB, which a CTA copies from global to shared memory.
 // The scan over the 8 entries of T_i reads the SAME addresses in every thread (broadcast LDS) and keeps one entry with
-// masks: no secret-dependent address or branch.
+// predicated selects: no secret-dependent address or branch.
 #pragma once
 #include "dh.cuh"
 
@@ -46,12 +46,12 @@ FQ_FN ptA3 a3_load(const u32* w) {
 FQ_FN ptA3 comb_select(const u32* tab, u32 idx, u32 neg) {
   u32 w[FQ_COMB_ENTRY_WORDS];
   FQ_UNROLL
-  for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] = 0;
+  for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] = tab[7 * FQ_COMB_ENTRY_WORDS + j];
   FQ_UNROLL
-  for (int e = 0; e < 8; e++) {
-    u32 m = (idx == (u32)e) ? 0xffffffffu : 0u;
+  for (int e = 0; e < 7; e++) {                      // one predicated select (SEL) per entry and word
+    const bool c = idx == (u32)e;
     FQ_UNROLL
-    for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] |= tab[e * FQ_COMB_ENTRY_WORDS + j] & m;
+    for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] = c ? tab[e * FQ_COMB_ENTRY_WORDS + j] : w[j];
   }
   ptA3 P = a3_load(w), R;
   R.N = fp2_select(neg, P.D, P.N); R.D = fp2_select(neg, P.N, P.D);

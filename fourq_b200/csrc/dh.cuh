@@ -4,7 +4,7 @@
 // Table residency.  T[i] = [2i+1]P in R2 is 8 x 4 x 32 B = 1 KiB per thread.  Entries 0..6 live in shared memory as
 // 128-bit words laid out [entry][quad][thread] (consecutive threads -> consecutive 16 B: conflict-free LDS.128/STS.128),
 // entry 7 stays in registers: 7 x 128 B x 128 threads = 112 KiB per CTA, two CTAs per SM.
-// Selection reads ALL entries and keeps one with AND/OR masks (LOP3); the sign is applied with masks too.
+// Selection issues the loads of ALL entries and keeps one by predicate (tab_select); the sign is applied with masks.
 #pragma once
 #include "codec.cuh"
 #include "scalar.cuh"
@@ -31,21 +31,37 @@ FQ_FN ptR2 tab_load(const TabView& T, int e) {
   return P;
 }
 
-FQ_FN void fp_or_masked(fp& acc, const fp& a, u32 m) {
-  acc.v[0] |= a.v[0] & m; acc.v[1] |= a.v[1] & m; acc.v[2] |= a.v[2] & m; acc.v[3] |= a.v[3] & m;
+// Constant-time table selection.  Every thread issues the loads of ALL entries in the same order from addresses that do not
+// depend on the digit; the digit only sets the predicate ("mask") of each load.
+//   default           masked loads: `@p ld.shared.v4` -- a lane whose predicate is off transfers nothing and keeps its
+//                     registers, so the select costs no ALU instruction at all (56 LDS.128 per select).
+//   FQ_STRICT_SELECT  every lane loads every entry and each word goes through one SEL per entry (56 LDS.128 + 224 SEL).
+// No secret-dependent branch or address in either; the layout [entry][quad][thread] keeps lane L on banks 4L..4L+3 for
+// every entry, so there is no digit-dependent bank conflict.
+FQ_FN void tab_take(const TabView& T, int e, int q, fp& w, bool c) {
+#if defined(FQ_HOSTSIM)
+  if (c) w = tab_get(T, e, q);
+#elif defined(FQ_STRICT_SELECT)
+  u32 a0, a1, a2, a3;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+               : "r"((u32)__cvta_generic_to_shared(T.base + (e * 8 + q) * T.stride)));
+  w.v[0] = c ? a0 : w.v[0]; w.v[1] = c ? a1 : w.v[1]; w.v[2] = c ? a2 : w.v[2]; w.v[3] = c ? a3 : w.v[3];
+#else
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4]; }"
+               : "+r"(w.v[0]), "+r"(w.v[1]), "+r"(w.v[2]), "+r"(w.v[3])
+               : "r"((u32)__cvta_generic_to_shared(T.base + (e * 8 + q) * T.stride)), "r"((u32)c));
+#endif
 }
-FQ_FN void r2_or_masked(ptR2& acc, const ptR2& a, u32 m) {
-  fp_or_masked(acc.N.re, a.N.re, m); fp_or_masked(acc.N.im, a.N.im, m); fp_or_masked(acc.D.re, a.D.re, m); fp_or_masked(acc.D.im, a.D.im, m);
-  fp_or_masked(acc.E.re, a.E.re, m); fp_or_masked(acc.E.im, a.E.im, m); fp_or_masked(acc.F.re, a.F.re, m); fp_or_masked(acc.F.im, a.F.im, m);
+FQ_FN void tab_take_r2(const TabView& T, int e, ptR2& w, bool c) {
+  tab_take(T, e, 0, w.N.re, c); tab_take(T, e, 1, w.N.im, c); tab_take(T, e, 2, w.D.re, c); tab_take(T, e, 3, w.D.im, c);
+  tab_take(T, e, 4, w.E.re, c); tab_take(T, e, 5, w.E.im, c); tab_take(T, e, 6, w.F.re, c); tab_take(T, e, 7, w.F.im, c);
 }
-FQ_FN ptR2 r2_zero() { ptR2 P; P.N = fp2_zero(); P.D = fp2_zero(); P.E = fp2_zero(); P.F = fp2_zero(); return P; }
 
-// constant-time T[idx]: scan of entries 0..6 in shared memory plus the register-resident entry 7
+// T[idx]: starts from the register-resident entry 7 and scans entries 0..6 in shared memory
 FQ_FN ptR2 tab_select(const TabView& T, const ptR2& T7, u32 idx) {
-  ptR2 S = r2_zero();
-  r2_or_masked(S, T7, (idx == 7) ? 0xffffffffu : 0u);
+  ptR2 S = T7;
   FQ_UNROLL
-  for (int e = 0; e < 7; e++) r2_or_masked(S, tab_load(T, e), (idx == (u32)e) ? 0xffffffffu : 0u);
+  for (int e = 0; e < 7; e++) tab_take_r2(T, e, S, idx == (u32)e);
   return S;
 }
 
@@ -123,12 +139,12 @@ struct SelectConst {
   FQ_MFN ptR2 operator()(u32 idx) const {
     u32 w[32];
     FQ_UNROLL
-    for (int j = 0; j < 32; j++) w[j] = 0;
+    for (int j = 0; j < 32; j++) w[j] = tab[7 * 32 + j];
     FQ_UNROLL
-    for (int e = 0; e < 8; e++) {
-      u32 m = (idx == (u32)e) ? 0xffffffffu : 0u;
+    for (int e = 0; e < 7; e++) {
+      const bool c = idx == (u32)e;
       FQ_UNROLL
-      for (int j = 0; j < 32; j++) w[j] |= tab[e * 32 + j] & m;
+      for (int j = 0; j < 32; j++) w[j] = c ? tab[e * 32 + j] : w[j];
     }
     ptR2 P;
     P.N = fp2_set(fp_set(w[0], w[1], w[2], w[3]), fp_set(w[4], w[5], w[6], w[7]));

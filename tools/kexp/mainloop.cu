@@ -14,9 +14,9 @@ __device__ __forceinline__ void ld8(const void* base, size_t row, u32* w) {
 template <int NSLOT> struct SelectSlots {
   TabView T;
   __device__ __forceinline__ ptR2 operator()(u32 idx) const {
-    ptR2 S = r2_zero();
+    ptR2 S = tab_load(T, 7 % NSLOT);
 #pragma unroll
-    for (int e = 0; e < 8; e++) r2_or_masked(S, tab_load(T, e % NSLOT), (idx == (u32)e) ? 0xffffffffu : 0u);
+    for (int e = 0; e < 7; e++) tab_take_r2(T, e % NSLOT, S, idx == (u32)e);
     return S;
   }
 };
@@ -67,6 +67,7 @@ int main() {
   void *k, *out; cudaMalloc(&k, n * 32); cudaMalloc(&out, n * 32);
   cudaMemset(k, 0x5a, n * 32);
   run<2, 7>("minb2 7slots", k, out, n);
+  run<2, 4>("minb2 4slots", k, out, n);
   run<3, 4>("minb3 4slots", k, out, n);
   return 0;
 }
