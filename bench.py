@@ -5,15 +5,16 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1, one rank per GPU)
 
 Workload (config.workload): BASELINE.json configs[2] -- variable-base DH, 2^20 (scalar, encoded point) rows per GPU:
-decode + validate + cofactor clearing + fixed-window scalar multiplication + inversion + encode, one kernel launch per
-step.  Every row is independent, so N GPUs run N independent slices (weak scaling, no collective on the data path;
+decode + validate + cofactor clearing + scalar multiplication + inversion + encode, three kernel launches per step
+(k_dh_prep -> k_dh_ladder -> k_dh_finish).  Every row is independent, so N GPUs run N independent slices (weak scaling, no collective on the data path;
 torch.distributed is used only for the barrier and the max-over-ranks of the timings).
 
 One JSON line is printed by rank 0:
   value      rows/s with inputs resident in HBM, CUDA-event time of the kernel, L2 flushed between steps
   e2e        the same rows through the public API fourq_b200.DH() from pinned host numpy arrays (H2D + kernels + D2H)
-  roofline   achieved = value x 103,836 algorithmic 32x32->64 multiply-adds per row ("tight" count of
-             decode + DH_windowed + encode) against the IMAD.WIDE.U32 issue peak measured live on the same GPU
+  roofline   dominant kernel k_dh_ladder: rows x algorithmic 32x32->64 multiply-adds of the main loop / its CUDA-event time,
+             against the IMAD.WIDE.U32 issue peak measured live on the same GPU; roofline.step is the same for the whole
+             step (SURVEY.md 8d "tight" count of decode + DH + encode: 58,284 endo / 103,836 windowed per row)
   cpu_baseline  the oracle (Python restatement of the reference) on the host's cores over a bounded sample; the same
              sample is compared bit-for-bit with the GPU output
 --impl reference times the reference's CPU algorithm (the oracle port: the reference itself is Python 2 and cannot run
@@ -36,8 +37,10 @@ sys.path.insert(0, ROOT)
 METRIC = "curve4q_variable_base_dh_scalar_mults_per_s"
 UNIT = "scalar-mults/s"
 ROWS_PER_GPU = 1 << 20
-# SURVEY.md 8d, tight counts of 32x32->64 multiply-adds per row of cfg 3 for the algorithm that is run
+# SURVEY.md 8d, tight counts of 32x32->64 multiply-adds per row of cfg 3 for the algorithm that is run ...
 IMADS_PER_ROW = {"windowed": 103836, "endo": 58284}
+# ... and the share of the dominant kernel k_dh_ladder (the main loop): 62 x (4 DBL + ADD) / 64 x (DBL + ADD), DBL = 272, ADD = 384
+IMADS_PER_ROW_LADDER = {"windowed": 62 * (4 * 272 + 384), "endo": 64 * (272 + 384)}
 BYTES_PER_ROW = 96              # 32 scalar + 32 point + 32 out
 WORKLOAD = "cfg3 variable-base DH (decode+validate+[392]P+[k]Q+inversion+encode), 2^20 (scalar, encoded point) rows per GPU"
 
@@ -58,13 +61,53 @@ def make_inputs(fq, rows, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """SM clock and throttle reasons of one GPU sampled every 10 ms (NVML, in-process) while the timed region runs;
+    falls back to an `nvidia-smi -lms 100` child process when pynvml is not importable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
         self.gpu, self.proc, self.lines = gpu, None, []
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        self.sm, self.mx, self.reasons = [], [], set()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap, so resolve through the PCI bus id when possible
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index(pynvml, gpu))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _nvml_index(pynvml, gpu):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x.strip() for x in vis.split(",") if x.strip() != ""]
+        if ids and all(x.isdigit() for x in ids) and gpu < len(ids):
+            return int(ids[gpu])
+        return gpu
+
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.handle))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -77,6 +120,11 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, 10 ms period, during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -95,7 +143,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------- CPU arm (oracle port of the reference)
@@ -115,7 +163,7 @@ def cpu_dh(k, pub, procs, algorithm):
     return res, dt
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host cores, bounded sample per step."""
     if rank != 0:
         return
@@ -142,10 +190,19 @@ def run_reference(args, rank):
                              "sample": "%d rows per step x %d steps, oracle/fourq_oracle.py row_dh (DH_%s) under multiprocessing" % (sample, args.steps, args.algorithm)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ---------------------------------------------------------------- GPU arm
+
+def _quiet_stdout():
+    """Points fd 1 at stderr for the rest of the run (NCCL and other libraries print banners to stdout) and returns a file
+    on the original stdout, so that the JSON line is the only thing the caller's stdout ever sees."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -158,12 +215,13 @@ def main():
                     help="scalar-multiplication algorithm of the reference: MUL_windowed or MUL_endo (same outputs)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="rows of the CPU baseline sample (default 256 per core; 0 = skip)")
     args = ap.parse_args()
+    out = _quiet_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, out)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -205,10 +263,11 @@ def main():
     barrier()
     sampler.start()
     t_wall0 = time.perf_counter()
-    kernel_ms = []
+    kernel_ms, phase_ms = [], []
     for _ in range(args.steps):
         fqdev.flush_l2(local_rank)                       # untimed: write 256 MiB > L2 between timed iterations
         kernel_ms.append(fqdev.dev_run(devop, local_rank, dk, dp, dout, dst, rows))   # CUDA events on the launch stream
+        phase_ms.append(fqdev.last_phase_ms())           # the same step's three kernels, one event pair each
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -236,27 +295,32 @@ def main():
     line = None
     if rank == 0:
         wide_peak, imad_peak = fqdev.imad_peak(local_rank)
-        achieved = (value / world) * imads
+        step_achieved = (value / world) * imads                      # all three kernels of a step
+        ph = [sum(p[i] for p in phase_ms) / len(phase_ms) for i in range(3)]      # rank 0's average ms: prepare, ladder, finish
+        ladder_achieved = rows * IMADS_PER_ROW_LADDER[args.algorithm] / (ph[1] * 1e-3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
-        traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        traffic = None        # dram__bytes_read.sum + dram__bytes_write.sum of one ladder launch, from the committed ncu --set full capture
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_dh_%s_2p20_rows_bytes" % args.algorithm)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_dh_ladder_%s_2p20_rows_bytes" % args.algorithm)
             if traffic is not None and rows != ROWS_PER_GPU:
                 traffic = None
         except (OSError, ValueError):
             pass
-        roofline = {"bound": "imad", "achieved": achieved / 1e12, "peak": wide_peak / 1e12, "unit": "T IMAD.WIDE/s", "frac": achieved / wide_peak,
-                    "traffic": traffic,
-                    "note": "per GPU; achieved = rows/s x %d algorithmic 32x32->64 multiply-adds per row (SURVEY 8d); peak = IMAD.WIDE.U32 "
-                            "issue rate measured live by fq_imad_peak (32-bit IMAD measured %.2f T/s); HBM is not the bound: "
-                            "%d B/row -> %.4f of %s %.1f GB/s" % (imads, imad_peak / 1e12, BYTES_PER_ROW,
-                                                                   (value / world) * BYTES_PER_ROW / 1e9 / hbm,
-                                                                   "measured" if peaks else "fallback", hbm)}
+        roofline = {"bound": "imad", "kernel": "k_dh_ladder", "achieved": ladder_achieved / 1e12, "peak": wide_peak / 1e12, "unit": "T IMAD.WIDE/s",
+                    "frac": ladder_achieved / wide_peak, "traffic": traffic,
+                    "kernel_ms": {"k_dh_prep": ph[0], "k_dh_ladder": ph[1], "k_dh_finish": ph[2]},
+                    "step": {"achieved": step_achieved / 1e12, "frac": step_achieved / wide_peak, "imads_per_row": imads},
+                    "note": "per GPU; dominant kernel k_dh_ladder: achieved = rows x %d algorithmic 32x32->64 multiply-adds per row of the main loop "
+                            "/ its CUDA-event time; step = all three kernels, rows/s x %d (SURVEY 8d, tight count of decode + DH + encode); peak = "
+                            "IMAD.WIDE.U32 issue rate measured live by fq_imad_peak (32-bit IMAD measured %.2f T/s); HBM is not the bound: "
+                            "%d B/row algorithmic + 2.3 KiB/row of scratch -> %.3f of %s %.1f GB/s" % (
+                                IMADS_PER_ROW_LADDER[args.algorithm], imads, imad_peak / 1e12, BYTES_PER_ROW,
+                                (value / world) * (BYTES_PER_ROW + 2 * 1156) / 1e9 / hbm, "measured" if peaks else "fallback", hbm)}
         cores = os.cpu_count() or 1
         sample = args.cpu_sample if args.cpu_sample >= 0 else 256 * cores
         cpu = None
@@ -273,17 +337,17 @@ def main():
                 "dtype": "u32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "algorithm": "MUL_%s (curve4q.py:%s)" % (args.algorithm, "405-442" if args.algorithm == "endo" else "188-235"),
                            "rows_per_gpu": rows, "l2": "flushed (256 MiB memset) between timed iterations",
-                           "timing": "CUDA events around each kernel launch, summed over steps, max over ranks", "wall_s_timed_region": wall},
+                           "timing": "CUDA events around the three kernels of each step (k_dh_prep, k_dh_ladder, k_dh_finish), summed over steps, max over ranks", "wall_s_timed_region": wall},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * rows, "d2h_bytes_per_step": 33 * rows,
                         "note": "fourq_b200.DH(k, B, out=, status=) on pinned numpy arrays (inputs and outputs), wall clock, per GPU bytes"},
-                "gpu_launches": args.steps,
+                "gpu_launches": 3 * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu}
     barrier()
     if dist is not None:
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
 
 
 if __name__ == "__main__":

@@ -50,7 +50,7 @@ def lib():
         "fq_dev_alloc": ([i, ctypes.POINTER(vp), sz], i), "fq_dev_free": ([i, vp], i),
         "fq_dev_upload": ([i, vp, vp, sz], i), "fq_dev_download": ([i, vp, vp, sz], i),
         "fq_dev_run": ([i, i, vp, vp, vp, vp, sz, i, ctypes.POINTER(ctypes.c_float)], i),
-        "fq_dev_flush_l2": ([i], i),
+        "fq_dev_flush_l2": ([i], i), "fq_dev_last_phase_ms": ([ctypes.POINTER(ctypes.c_float)], i),
         "fq_imad_peak": ([i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)], i),
     }
     for name, (argtypes, restype) in sigs.items():
@@ -64,7 +64,7 @@ EXPORTS = ["fq_version", "fq_device_count", "fq_last_error", "fq_set_device_base
            "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_decode", "fq_encode",
            "fq_dh", "fq_dh_affine", "fq_dh_base", "fq_mul_base", "fq_dh_endo", "fq_dh_endo_affine", "fq_dh_endo_base",
            "fq_mul_endo_base", "fq_dh_base_comb", "fq_mul_base_comb", "fq_x25519", "fq_host_alloc", "fq_host_free",
-           "fq_dev_alloc", "fq_dev_free", "fq_dev_upload", "fq_dev_download", "fq_dev_run", "fq_dev_flush_l2", "fq_imad_peak"]
+           "fq_dev_alloc", "fq_dev_free", "fq_dev_upload", "fq_dev_download", "fq_dev_run", "fq_dev_last_phase_ms", "fq_dev_flush_l2", "fq_imad_peak"]
 
 
 def check(rc):

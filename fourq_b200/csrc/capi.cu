@@ -7,6 +7,7 @@
 // grow on demand; nothing else is cached between calls.  There is no CPU implementation of any operation here.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -22,6 +23,7 @@ constexpr size_t kFlushBytes = 256u << 20;      // > 126 MB L2
 
 thread_local char tl_err[512] = "";
 thread_local float tl_kernel_ms = 0.f;
+thread_local float tl_phase_ms[3] = {0.f, 0.f, 0.f};
 std::mutex g_mu;
 int g_dev_base = 0;
 
@@ -40,6 +42,8 @@ struct DevCtx {
   Slot slot[kStreams];
   void* flush = nullptr;
   void* comb = nullptr;       // per-digit fixed-base tables (kernels_comb.cu)
+  void* dh_scratch[kStreams] = {nullptr, nullptr, nullptr};     // table / plan / projective result of the DH kernels
+  size_t dh_scratch_cap[kStreams] = {0, 0, 0};
   int sms = 0;
 };
 DevCtx g_ctx[kMaxDev];
@@ -72,8 +76,32 @@ int slot_reserve(Slot& s, int which, size_t bytes) {
   return FQ_OK;
 }
 
+// grows the DH scratch of stream slot `si` to hold `rows` rows
+int dh_scratch_reserve(DevCtx& c, int si, size_t rows) {
+  size_t bytes = fqk_dh_scratch_bytes(rows);
+  if (bytes <= c.dh_scratch_cap[si]) return FQ_OK;
+  if (c.dh_scratch[si]) CU(cudaFree(c.dh_scratch[si]));
+  c.dh_scratch[si] = nullptr; c.dh_scratch_cap[si] = 0;
+  CU(cudaMalloc(&c.dh_scratch[si], bytes));
+  c.dh_scratch_cap[si] = bytes;
+  return FQ_OK;
+}
+bool is_dh_op(int op) { return op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE || op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE; }
+
 // bytes per row of each operand of an operation
 struct OpDesc { int op; int a_bytes, b_bytes, out_bytes; bool status; size_t chunk_rows; };
+
+// rows per pipeline chunk of the variable-base DH ops: a whole number of k_dh_ladder waves (2 CTAs x 128 rows per SM) keeps
+// the tail of each chunk short; FQ_DH_CHUNK_ROWS overrides it (tuning knob, read once).
+size_t dh_chunk_rows() {
+  static size_t v = 0;
+  if (v == 0) {
+    const char* e = getenv("FQ_DH_CHUNK_ROWS");
+    long long x = e ? atoll(e) : 0;
+    v = x >= 128 ? (size_t)x : (size_t)1 << 17;
+  }
+  return v;
+}
 
 OpDesc describe(int op) {
   switch (op) {
@@ -82,8 +110,8 @@ OpDesc describe(int op) {
     case FQ_DEVOP_FP2_INV: return {op, 32, 0, 32, false, (size_t)1 << 18};
     case FQ_DEVOP_DECODE: return {op, 32, 0, 64, true, (size_t)1 << 18};
     case FQ_DEVOP_ENCODE: return {op, 64, 0, 32, false, (size_t)1 << 20};
-    case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, 32, 32, 32, true, (size_t)1 << 17};
-    case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, (size_t)1 << 17};
+    case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, 32, 32, 32, true, dh_chunk_rows()};
+    case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, dh_chunk_rows()};
     case FQ_DEVOP_DH_BASE: case FQ_DEVOP_DH_ENDO_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
     case FQ_DEVOP_MUL_BASE: case FQ_DEVOP_MUL_ENDO_BASE: return {op, 32, 0, 32, false, (size_t)1 << 17};
     case FQ_DEVOP_DH_BASE_COMB: return {op, 32, 0, 32, true, (size_t)1 << 18};
@@ -93,7 +121,8 @@ OpDesc describe(int op) {
   }
 }
 
-cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s) {
+// si: stream slot whose DH scratch is used (reserved by the caller); ev: optional per-kernel events of the DH pipeline
+cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s, int si = 0, cudaEvent_t* ev = nullptr) {
   switch (op) {
     case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, cx.comb, a, out, status, n, cx.sms, s);
     case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, cx.comb, a, out, nullptr, n, cx.sms, s);
@@ -106,12 +135,12 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_FP2_CONJ: return fqk_fp2_op(FQK_CONJ, a, b, out, n, s);
     case FQ_DEVOP_DECODE: return fqk_decode(a, out, status, n, s);
     case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
-    case FQ_DEVOP_DH: return fqk_dh(0, 0, a, b, out, status, n, s);
-    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, a, b, out, status, n, s);
+    case FQ_DEVOP_DH: return fqk_dh(0, 0, a, b, out, status, n, cx.dh_scratch[si], s, ev);
+    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, a, out, status, n, s);
     case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, a, out, nullptr, n, s);
-    case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, a, b, out, status, n, s);
-    case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, a, b, out, status, n, s);
+    case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, a, b, out, status, n, cx.dh_scratch[si], s, ev);
+    case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, a, out, status, n, s);
     case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, a, out, nullptr, n, s);
     case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, s);
@@ -152,12 +181,13 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* 
       if (d.b_bytes && (rc = slot_reserve(s, 1, d.chunk_rows * d.b_bytes)) != FQ_OK) break;
       if ((rc = slot_reserve(s, 2, d.chunk_rows * d.out_bytes)) != FQ_OK) break;
       if (d.status && (rc = slot_reserve(s, 3, d.chunk_rows)) != FQ_OK) break;
+      if (is_dh_op(op) && (rc = dh_scratch_reserve(cx, si, d.chunk_rows)) != FQ_OK) break;
       CU(cudaMemcpyAsync(s.buf[0], a + r0 * d.a_bytes, rows * d.a_bytes, cudaMemcpyHostToDevice, st));
       if (d.b_bytes) CU(cudaMemcpyAsync(s.buf[1], b + r0 * d.b_bytes, rows * d.b_bytes, cudaMemcpyHostToDevice, st));
       ChunkEv ev; ev.dev = i;
       CU(cudaEventCreate(&ev.e0)); CU(cudaEventCreate(&ev.e1));
       CU(cudaEventRecord(ev.e0, st));
-      CU(launch(cx, op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st));
+      CU(launch(cx, op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st, si));
       CU(cudaEventRecord(ev.e1, st));
       evs.push_back(ev);
       CU(cudaMemcpyAsync(out + r0 * d.out_bytes, s.buf[2], rows * d.out_bytes, cudaMemcpyDeviceToHost, st));
@@ -268,17 +298,29 @@ int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* s
   std::lock_guard<std::mutex> lock(g_mu);
   int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
   if (describe(op).op < 0 || iters < 1) return fail(FQ_ERR_ARG, "bad op/iters");
-  cudaStream_t st = g_ctx[dev].st[0];
-  cudaEvent_t e0, e1;
+  DevCtx& cx = g_ctx[dev];
+  cudaStream_t st = cx.st[0];
+  const bool dh = is_dh_op(op);
+  if (dh && (rc = dh_scratch_reserve(cx, 0, n)) != FQ_OK) return rc;
+  cudaEvent_t e0, e1, ph[4];
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ph[i]));
   CU(cudaEventRecord(e0, st));
-  for (int i = 0; i < iters; i++) CU(launch(g_ctx[dev], op, a, b, out, status, n, st));
+  for (int i = 0; i < iters; i++) CU(launch(cx, op, a, b, out, status, n, st, 0, (dh && i == iters - 1) ? ph : nullptr));
   CU(cudaEventRecord(e1, st));
   CU(cudaEventSynchronize(e1));
   float t = 0.f;
   CU(cudaEventElapsedTime(&t, e0, e1));
+  tl_phase_ms[0] = tl_phase_ms[1] = tl_phase_ms[2] = 0.f;
+  if (dh && n > 0) for (int i = 0; i < 3; i++) CU(cudaEventElapsedTime(&tl_phase_ms[i], ph[i], ph[i + 1]));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ph[i]);
   if (ms) *ms = t / iters;
+  return FQ_OK;
+}
+int fq_dev_last_phase_ms(float* ms3) {
+  if (!ms3) return fail(FQ_ERR_ARG, "null pointer");
+  for (int i = 0; i < 3; i++) ms3[i] = tl_phase_ms[i];
   return FQ_OK;
 }
 int fq_dev_flush_l2(int dev) {

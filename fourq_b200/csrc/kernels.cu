@@ -112,12 +112,16 @@ cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s) {
   k_encode<<<grid_for(n, 256), 256, 0, s>>>(xy, enc, n);
   return cudaGetLastError();
 }
-cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s) {
-  int dev = 0, sms = 0;
-  cudaError_t e;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  return endo ? fqk_dh_endo(affine, k, pt, out, status, n, sms, s) : fqk_dh_windowed(affine, k, pt, out, status, n, sms, s);
+size_t fqk_dh_scratch_bytes(size_t n) {
+  // kernels_dh.cuh: (64 table + 2 digit-register + 6 result) quads of 16 B and one meta word per row, rows padded to 128,
+  // at most 2^22 rows per launch group
+  size_t rows = n < ((size_t)1 << 22) ? n : ((size_t)1 << 22);
+  size_t npad = (rows + 127) / 128 * 128;
+  return npad * (72 * 16 + 4);
+}
+cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev) {
+  if (n == 0) return cudaSuccess;
+  return endo ? fqk_dh_endo(affine, k, pt, out, status, n, scratch, s, ev) : fqk_dh_windowed(affine, k, pt, out, status, n, scratch, s, ev);
 }
 cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;

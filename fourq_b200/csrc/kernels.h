@@ -9,12 +9,16 @@ cudaError_t fqk_device_init(cudaStream_t s);   // once per device: fixed-base ta
 cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_decode(const void* enc, void* xy, void* status, size_t n, cudaStream_t s);
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s);
-cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, cudaStream_t s);
+// variable-base DH = three kernels (prepare, ladder, finish; kernels_dh.cuh) that hand the per-row table and the projective
+// result over through `scratch`, a device buffer of at least fqk_dh_scratch_bytes(n) bytes owned by the caller.
+// ev: optional array of 4 events recorded before/between/after the three kernels (per-kernel timing).
+size_t fqk_dh_scratch_bytes(size_t n);
+cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev);
 // per-algorithm translation units (kernels_dh_windowed.cu, kernels_dh_endo.cu)
 cudaError_t fqk_dh_windowed_init();
 cudaError_t fqk_dh_endo_init();
-cudaError_t fqk_dh_windowed(int affine, const void* k, const void* pt, void* out, void* status, size_t n, int sms, cudaStream_t s);
-cudaError_t fqk_dh_endo(int affine, const void* k, const void* pt, void* out, void* status, size_t n, int sms, cudaStream_t s);
+cudaError_t fqk_dh_windowed(int affine, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev);
+cudaError_t fqk_dh_endo(int affine, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev);
 cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s);
 // fixed-base per-digit tables (kernels_comb.cu): tabs is the device buffer returned by fqk_comb_init
 cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s);

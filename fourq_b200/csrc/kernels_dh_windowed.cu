@@ -1,6 +1,6 @@
-// kernels_dh_windowed.cu -- k_dh with MUL_windowed (curve4q.py:188-235); see kernels_dh.cuh
+// kernels_dh_windowed.cu -- the DH kernels with MUL_windowed (curve4q.py:188-235); see kernels_dh.cuh
 #include "kernels_dh.cuh"
 cudaError_t fqk_dh_windowed_init() { return dh_init<false>(); }
-cudaError_t fqk_dh_windowed(int affine, const void* k, const void* pt, void* out, void* status, size_t n, int sms, cudaStream_t s) {
-  return dh_launch<false>(affine, k, pt, out, status, n, sms, s);
+cudaError_t fqk_dh_windowed(int affine, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev) {
+  return dh_launch<false>(affine, k, pt, out, status, n, scratch, s, ev);
 }

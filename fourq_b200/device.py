@@ -91,6 +91,13 @@ def dev_run(op, dev, a, b, out, status, n, iters=1):
     return float(ms.value)
 
 
+def last_phase_ms():
+    """CUDA-event milliseconds of the (prepare, ladder, finish) kernels of the last launch of the last DH dev_run."""
+    ms = (ctypes.c_float * 3)()
+    _lib.check(_lib.lib().fq_dev_last_phase_ms(ms))
+    return [float(x) for x in ms]
+
+
 def flush_l2(dev):
     _lib.check(_lib.lib().fq_dev_flush_l2(int(dev)))
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 101
+#define FQ_VERSION 102
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -131,6 +131,9 @@ FQ_API int fq_dev_free(int dev, void* p);
 FQ_API int fq_dev_upload(int dev, void* dst, const void* src, size_t bytes);
 FQ_API int fq_dev_download(int dev, void* dst, const void* src, size_t bytes);
 FQ_API int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* status, size_t n, int iters, float* ms);
+/* CUDA-event milliseconds of the three kernels (prepare, ladder, finish) of the last launch of the last fq_dev_run of
+ * this thread with a variable-base DH op (FQ_DEVOP_DH, _DH_AFFINE, _DH_ENDO, _DH_ENDO_AFFINE); zeros otherwise. */
+FQ_API int fq_dev_last_phase_ms(float* ms3);
 /* writes `bytes` of zeros over a scratch buffer larger than L2 (used between timed iterations) */
 FQ_API int fq_dev_flush_l2(int dev);
 

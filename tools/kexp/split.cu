@@ -1,0 +1,163 @@
+// split.cu -- developer experiment: the DH row as three kernels (prepare at high occupancy -> ladder with the table in
+// shared memory -> finish with an inversion shared by several rows of a thread) against the fused k_dh kernel.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o split split.cu && ./split
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../fourq_b200/csrc/kernels_dh.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+struct Scratch { uint4* tab; uint4* plan; u32* meta; uint4* R; size_t npad; };
+
+__device__ __forceinline__ void stq(uint4* p, const fp& a) { *p = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+__device__ __forceinline__ fp ldq(const uint4* p) { uint4 w = *p; return fp_set(w.x, w.y, w.z, w.w); }
+
+template <bool ENDO, int MINB> __global__ void __launch_bounds__(128, MINB)
+k_prep(const void* __restrict__ k, const void* __restrict__ pt, Scratch sc, size_t n) {
+  size_t row = (size_t)blockIdx.x * 128 + threadIdx.x;
+  size_t src = row < n ? row : n - 1;
+  TabView T; T.base = sc.tab + row; T.stride = (u32)sc.npad;
+  u32 wk[8], wp[8];
+  ld8(k, src, wk); ld8(pt, src, wp);
+  DhState D;
+  u32 st = row_dh_setup<ENDO, false>(wk, wp, T, D);
+  tab_store(T, 7, D.T7);
+  sc.plan[row] = make_uint4(D.plan.S.v[0], D.plan.S.v[1], D.plan.S.v[2], D.plan.S.v[3]);
+  sc.plan[sc.npad + row] = make_uint4(D.plan.S.v[4], D.plan.S.v[5], D.plan.S.v[6], D.plan.S.v[7]);
+  sc.meta[row] = D.plan.first | (st << 8);
+}
+
+template <bool ENDO> __global__ void __launch_bounds__(128, 2)
+k_ladder(Scratch sc, size_t n) {
+  extern __shared__ uint4 smem[];
+  size_t row = (size_t)blockIdx.x * 128 + threadIdx.x;
+  TabView T; T.base = smem + threadIdx.x; T.stride = 128;
+  const uint4* g = sc.tab + row;
+#pragma unroll 8
+  for (int i = 0; i < 56; i++) T.base[i * 128] = g[(size_t)i * sc.npad];
+  DhState D;
+  { TabView G; G.base = sc.tab + row; G.stride = (u32)sc.npad; D.T7 = tab_load(G, 7); }
+  uint4 s0 = sc.plan[row], s1 = sc.plan[sc.npad + row];
+  D.plan.S.v[0] = s0.x; D.plan.S.v[1] = s0.y; D.plan.S.v[2] = s0.z; D.plan.S.v[3] = s0.w;
+  D.plan.S.v[4] = s1.x; D.plan.S.v[5] = s1.y; D.plan.S.v[6] = s1.z; D.plan.S.v[7] = s1.w;
+  D.plan.first = sc.meta[row] & 0xff;
+  ptR1 R = row_dh_loop<ENDO>(T, D);
+  uint4* o = sc.R + row;
+  stq(o, R.X.re); stq(o + sc.npad, R.X.im); stq(o + 2 * sc.npad, R.Y.re); stq(o + 3 * sc.npad, R.Y.im);
+  stq(o + 4 * sc.npad, R.Z.re); stq(o + 5 * sc.npad, R.Z.im);
+}
+
+// RB rows per thread share one inversion (Montgomery's trick): prefix products, one fp2_inv, back-substitution
+template <int RB> __global__ void __launch_bounds__(128)
+k_finish(Scratch sc, void* __restrict__ out, unsigned char* __restrict__ status, size_t n) {
+  const size_t stride = (size_t)gridDim.x * 128;
+  const size_t t = (size_t)blockIdx.x * 128 + threadIdx.x;
+  fp2 pre[RB];
+  fp2 acc = fp2_one();
+#pragma unroll
+  for (int j = 0; j < RB; j++) {
+    size_t row = t + j * stride;
+    fp2 z = fp2_one();
+    if (row < n) { const uint4* o = sc.R + row; z = fp2_set(ldq(o + 4 * sc.npad), ldq(o + 5 * sc.npad)); }
+    bool zero = fp_is_zero(z.re) & fp_is_zero(z.im);
+    if (zero) z = fp2_one();
+    acc = (j == 0) ? z : fp2_mul(acc, z);
+    pre[j] = acc;
+  }
+  fp2 inv = fp2_inv(acc);
+#pragma unroll
+  for (int j = RB - 1; j >= 0; j--) {
+    size_t row = t + j * stride;
+    fp2 z = fp2_one(), X = fp2_zero(), Y = fp2_one();
+    if (row < n) {
+      const uint4* o = sc.R + row;
+      X = fp2_set(ldq(o), ldq(o + sc.npad)); Y = fp2_set(ldq(o + 2 * sc.npad), ldq(o + 3 * sc.npad));
+      z = fp2_set(ldq(o + 4 * sc.npad), ldq(o + 5 * sc.npad));
+    }
+    bool zero = fp_is_zero(z.re) & fp_is_zero(z.im);
+    if (zero) z = fp2_one();
+    fp2 zi = (j == 0) ? inv : fp2_mul(inv, pre[j - 1]);
+    if (j > 0) inv = fp2_mul(inv, z);
+    fp2b Zi = fp2_prep(zi);
+    fp2 ox = fp2_canon(fp2_mul_prep(X, Zi)), oy = fp2_canon(fp2_mul_prep(Y, Zi));
+    if (row < n) {
+      u32 st = sc.meta[row] >> 8;
+      bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());
+      if (st == FQ_ST_OK && neutral) st = FQ_ST_NEUTRAL;
+      u32 wo[8];
+      if (st == FQ_ST_OK) pt_encode(ox, oy, wo); else row_zero(wo, 8);
+      status[row] = (unsigned char)st;
+      st8(out, row, wo);
+    }
+  }
+}
+
+// inputs: valid encoded points = encode of k_dh<affine> outputs on G
+__global__ void k_fill_g(uint4* xy, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 w[16]; row_store_fp2(w, curve_gx()); row_store_fp2(w + 8, curve_gy());
+  for (int i = 0; i < 4; i++) xy[4 * row + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+__global__ void k_enc(const void* xy, void* enc, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wi[16], wo[8]; ld8(xy, 2 * row, wi); ld8(xy, 2 * row + 1, wi + 8); row_encode(wi, wo); st8(enc, row, wo);
+}
+
+template <class F> float timeit(F f, int reps = 3) {
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e9f;
+  for (int r = 0; r < reps; r++) { cudaEventRecord(e0); f(); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms; }
+  CK(cudaGetLastError());
+  return best;
+}
+
+template <bool ENDO> void run(size_t n, const void* k, const void* pub, void* out_ref, unsigned char* st_ref, void* out, unsigned char* st, Scratch sc) {
+  CK(cudaFuncSetAttribute(k_dh<false, ENDO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM));
+  CK(cudaFuncSetAttribute(k_ladder<ENDO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM));
+  unsigned g = (unsigned)(n / 128);
+  float t_fused = timeit([&] { k_dh<false, ENDO><<<g, 128, FQ_DH_SMEM>>>(k, pub, out_ref, st_ref, n); });
+  float tp2 = timeit([&] { k_prep<ENDO, 2><<<g, 128>>>(k, pub, sc, n); });
+  float tp3 = timeit([&] { k_prep<ENDO, 3><<<g, 128>>>(k, pub, sc, n); });
+  float tp4 = timeit([&] { k_prep<ENDO, 4><<<g, 128>>>(k, pub, sc, n); });
+  float tl = timeit([&] { k_ladder<ENDO><<<g, 128, FQ_DH_SMEM>>>(sc, n); });
+  float tf1 = timeit([&] { k_finish<1><<<g, 128>>>(sc, out, st, n); });
+  float tf4 = timeit([&] { k_finish<4><<<g / 4, 128>>>(sc, out, st, n); });
+  float tf8 = timeit([&] { k_finish<8><<<g / 8, 128>>>(sc, out, st, n); });
+  float tf16 = timeit([&] { k_finish<16><<<g / 16, 128>>>(sc, out, st, n); });
+  std::vector<unsigned char> a(n * 32), b(n * 32), sa(n), sb(n);
+  CK(cudaMemcpy(a.data(), out_ref, n * 32, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), out, n * 32, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sa.data(), st_ref, n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(sb.data(), st, n, cudaMemcpyDeviceToHost));
+  size_t bad = 0, nz = 0;
+  for (size_t i = 0; i < n; i++) { if (memcmp(&a[32 * i], &b[32 * i], 32) || sa[i] != sb[i]) bad++; if (sa[i]) nz++; }
+  float best_p = tp2 < tp3 ? tp2 : tp3; if (tp4 < best_p) best_p = tp4;
+  float best_f = tf4 < tf8 ? tf4 : tf8; if (tf16 < best_f) best_f = tf16;
+  printf("%s n=%zu fused %.3f ms | prep minb2 %.3f minb3 %.3f minb4 %.3f | ladder %.3f | finish rb1 %.3f rb4 %.3f rb8 %.3f rb16 %.3f | split best sum %.3f ms (%.1f%% of fused) | mismatches %zu, nonzero status %zu\n",
+         ENDO ? "endo" : "windowed", n, t_fused, tp2, tp3, tp4, tl, tf1, tf4, tf8, tf16, best_p + tl + best_f, 100.f * (best_p + tl + best_f) / t_fused, bad, nz);
+}
+
+int main() {
+  size_t n = 1 << 20;
+  void *k, *xy, *xy2, *pub, *out_ref, *out; unsigned char *st_ref, *st;
+  CK(cudaMalloc(&k, n * 32)); CK(cudaMalloc(&xy, n * 64)); CK(cudaMalloc(&xy2, n * 64)); CK(cudaMalloc(&pub, n * 32));
+  CK(cudaMalloc(&out_ref, n * 32)); CK(cudaMalloc(&out, n * 32)); CK(cudaMalloc(&st_ref, n)); CK(cudaMalloc(&st, n));
+  std::vector<unsigned> h(n * 8);
+  unsigned x = 12345; for (auto& v : h) { x = x * 1664525u + 1013904223u; v = x ^ (x >> 13); }
+  CK(cudaMemcpy(k, h.data(), n * 32, cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(k_dh<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM));
+  k_fill_g<<<(unsigned)(n / 256), 256>>>((uint4*)xy, n);
+  k_dh<true, true><<<(unsigned)(n / 128), 128, FQ_DH_SMEM>>>(k, xy, xy2, st, n);     // [392 k]G, affine
+  k_enc<<<(unsigned)(n / 256), 256>>>(xy2, pub, n);
+  // a few undecodable rows to exercise the status path
+  CK(cudaMemset((char*)pub + 32 * 1000, 0xff, 64)); CK(cudaMemset((char*)pub + 32 * 5000, 0x00, 32));
+  for (auto& v : h) { x = x * 1664525u + 1013904223u; v = x ^ (x >> 11); }
+  CK(cudaMemcpy(k, h.data(), n * 32, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  Scratch sc; sc.npad = n;
+  CK(cudaMalloc(&sc.tab, n * 64 * 16)); CK(cudaMalloc(&sc.plan, n * 2 * 16)); CK(cudaMalloc(&sc.meta, n * 4)); CK(cudaMalloc(&sc.R, n * 6 * 16));
+  run<true>(n, k, pub, out_ref, st_ref, out, st, sc);
+  run<false>(n, k, pub, out_ref, st_ref, out, st, sc);
+  return 0;
+}
