@@ -42,7 +42,7 @@ struct DevCtx {
   Slot slot[kStreams];
   void* flush = nullptr;
   void* comb = nullptr;       // per-digit fixed-base tables (kernels_comb.cu)
-  void* dh_scratch[kStreams] = {nullptr, nullptr, nullptr};     // table / plan / projective result of the DH kernels
+  void* dh_scratch[kStreams] = {nullptr, nullptr, nullptr};     // table / plan / projective result handed between the DH (and comb) kernels
   size_t dh_scratch_cap[kStreams] = {0, 0, 0};
   int sms = 0;
 };
@@ -76,9 +76,13 @@ int slot_reserve(Slot& s, int which, size_t bytes) {
   return FQ_OK;
 }
 
-// grows the DH scratch of stream slot `si` to hold `rows` rows
-int dh_scratch_reserve(DevCtx& c, int si, size_t rows) {
-  size_t bytes = fqk_dh_scratch_bytes(rows);
+bool is_dh_op(int op) { return op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE || op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE; }
+bool is_comb_op(int op) { return op == FQ_DEVOP_DH_BASE_COMB || op == FQ_DEVOP_MUL_BASE_COMB; }
+bool needs_scratch(int op) { return is_dh_op(op) || is_comb_op(op); }
+
+// grows the kernel scratch of stream slot `si` to what `op` needs for `rows` rows
+int dh_scratch_reserve(DevCtx& c, int si, int op, size_t rows) {
+  size_t bytes = is_comb_op(op) ? fqk_comb_scratch_bytes(rows) : fqk_dh_scratch_bytes(rows);
   if (bytes <= c.dh_scratch_cap[si]) return FQ_OK;
   if (c.dh_scratch[si]) CU(cudaFree(c.dh_scratch[si]));
   c.dh_scratch[si] = nullptr; c.dh_scratch_cap[si] = 0;
@@ -86,8 +90,6 @@ int dh_scratch_reserve(DevCtx& c, int si, size_t rows) {
   c.dh_scratch_cap[si] = bytes;
   return FQ_OK;
 }
-bool is_dh_op(int op) { return op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE || op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE; }
-
 // bytes per row of each operand of an operation
 struct OpDesc { int op; int a_bytes, b_bytes, out_bytes; bool status; size_t chunk_rows; };
 
@@ -124,8 +126,8 @@ OpDesc describe(int op) {
 // si: stream slot whose DH scratch is used (reserved by the caller); ev: optional per-kernel events of the DH pipeline
 cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s, int si = 0, cudaEvent_t* ev = nullptr) {
   switch (op) {
-    case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, cx.comb, a, out, status, n, cx.sms, s);
-    case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, cx.comb, a, out, nullptr, n, cx.sms, s);
+    case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, cx.comb, a, out, status, n, cx.dh_scratch[si], cx.sms, s);
+    case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, cx.comb, a, out, nullptr, n, cx.dh_scratch[si], cx.sms, s);
     case FQ_DEVOP_FP2_MUL: return fqk_fp2_op(FQK_MUL, a, b, out, n, s);
     case FQ_DEVOP_FP2_SQR: return fqk_fp2_op(FQK_SQR, a, b, out, n, s);
     case FQ_DEVOP_FP2_INV: return fqk_fp2_op(FQK_INV, a, b, out, n, s);
@@ -181,7 +183,7 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* 
       if (d.b_bytes && (rc = slot_reserve(s, 1, d.chunk_rows * d.b_bytes)) != FQ_OK) break;
       if ((rc = slot_reserve(s, 2, d.chunk_rows * d.out_bytes)) != FQ_OK) break;
       if (d.status && (rc = slot_reserve(s, 3, d.chunk_rows)) != FQ_OK) break;
-      if (is_dh_op(op) && (rc = dh_scratch_reserve(cx, si, d.chunk_rows)) != FQ_OK) break;
+      if (needs_scratch(op) && (rc = dh_scratch_reserve(cx, si, op, d.chunk_rows)) != FQ_OK) break;
       CU(cudaMemcpyAsync(s.buf[0], a + r0 * d.a_bytes, rows * d.a_bytes, cudaMemcpyHostToDevice, st));
       if (d.b_bytes) CU(cudaMemcpyAsync(s.buf[1], b + r0 * d.b_bytes, rows * d.b_bytes, cudaMemcpyHostToDevice, st));
       ChunkEv ev; ev.dev = i;
@@ -301,7 +303,7 @@ int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* s
   DevCtx& cx = g_ctx[dev];
   cudaStream_t st = cx.st[0];
   const bool dh = is_dh_op(op);
-  if (dh && (rc = dh_scratch_reserve(cx, 0, n)) != FQ_OK) return rc;
+  if (needs_scratch(op) && (rc = dh_scratch_reserve(cx, 0, op, n)) != FQ_OK) return rc;
   cudaEvent_t e0, e1, ph[4];
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ph[i]));

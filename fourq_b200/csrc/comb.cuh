@@ -42,18 +42,22 @@ FQ_FN ptA3 a3_load(const u32* w) {
   return P;
 }
 
-// constant-time T_i[idx] with the sign applied (curve4q.py:193-195: -(N, D, F) = (D, N, -F)); tab = the 192 words of T_i
+// constant-time T_i[idx] with the sign applied (curve4q.py:193-195: -(N, D, F) = (D, N, -F)); tab = the 192 words of T_i in
+// shared memory (16-byte aligned).  Entry 7 is loaded unconditionally, entries 0..6 under the digit's predicate (dh.cuh
+// quad_take): 6 LDS.128 per entry, the same addresses in every thread (broadcast).
 FQ_FN ptA3 comb_select(const u32* tab, u32 idx, u32 neg) {
-  u32 w[FQ_COMB_ENTRY_WORDS];
+  const uint4* t4 = reinterpret_cast<const uint4*>(tab);
+  fp w[6];
   FQ_UNROLL
-  for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] = tab[7 * FQ_COMB_ENTRY_WORDS + j];
+  for (int q = 0; q < 6; q++) { uint4 v = t4[7 * 6 + q]; w[q] = fp_set(v.x, v.y, v.z, v.w); }
   FQ_UNROLL
-  for (int e = 0; e < 7; e++) {                      // one predicated select (SEL) per entry and word
+  for (int e = 0; e < 7; e++) {
     const bool c = idx == (u32)e;
     FQ_UNROLL
-    for (int j = 0; j < FQ_COMB_ENTRY_WORDS; j++) w[j] = c ? tab[e * FQ_COMB_ENTRY_WORDS + j] : w[j];
+    for (int q = 0; q < 6; q++) quad_take(t4 + e * 6 + q, w[q], c);
   }
-  ptA3 P = a3_load(w), R;
+  ptA3 P, R;
+  P.N = fp2_set(w[0], w[1]); P.D = fp2_set(w[2], w[3]); P.F = fp2_set(w[4], w[5]);
   R.N = fp2_select(neg, P.D, P.N); R.D = fp2_select(neg, P.N, P.D);
   R.F.re = fp_set(P.F.re.v[0] ^ neg, P.F.re.v[1] ^ neg, P.F.re.v[2] ^ neg, P.F.re.v[3] ^ (neg & FQ_P3));
   R.F.im = fp_set(P.F.im.v[0] ^ neg, P.F.im.v[1] ^ neg, P.F.im.v[2] ^ neg, P.F.im.v[3] ^ (neg & FQ_P3));

@@ -38,20 +38,20 @@ FQ_FN ptR2 tab_load(const TabView& T, int e) {
 //   FQ_STRICT_SELECT  every lane loads every entry and each word goes through one SEL per entry (56 LDS.128 + 224 SEL).
 // No secret-dependent branch or address in either; the layout [entry][quad][thread] keeps lane L on banks 4L..4L+3 for
 // every entry, so there is no digit-dependent bank conflict.
-FQ_FN void tab_take(const TabView& T, int e, int q, fp& w, bool c) {
+// w = c ? *p : w for one 16-byte quad; p points into shared memory
+FQ_FN void quad_take(const uint4* p, fp& w, bool c) {
 #if defined(FQ_HOSTSIM)
-  if (c) w = tab_get(T, e, q);
+  if (c) w = fp_set(p->x, p->y, p->z, p->w);
 #elif defined(FQ_STRICT_SELECT)
   u32 a0, a1, a2, a3;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
-               : "r"((u32)__cvta_generic_to_shared(T.base + (e * 8 + q) * T.stride)));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"((u32)__cvta_generic_to_shared(p)));
   w.v[0] = c ? a0 : w.v[0]; w.v[1] = c ? a1 : w.v[1]; w.v[2] = c ? a2 : w.v[2]; w.v[3] = c ? a3 : w.v[3];
 #else
   asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4]; }"
-               : "+r"(w.v[0]), "+r"(w.v[1]), "+r"(w.v[2]), "+r"(w.v[3])
-               : "r"((u32)__cvta_generic_to_shared(T.base + (e * 8 + q) * T.stride)), "r"((u32)c));
+               : "+r"(w.v[0]), "+r"(w.v[1]), "+r"(w.v[2]), "+r"(w.v[3]) : "r"((u32)__cvta_generic_to_shared(p)), "r"((u32)c));
 #endif
 }
+FQ_FN void tab_take(const TabView& T, int e, int q, fp& w, bool c) { quad_take(T.base + (e * 8 + q) * T.stride, w, c); }
 FQ_FN void tab_take_r2(const TabView& T, int e, ptR2& w, bool c) {
   tab_take(T, e, 0, w.N.re, c); tab_take(T, e, 1, w.N.im, c); tab_take(T, e, 2, w.D.re, c); tab_take(T, e, 3, w.D.im, c);
   tab_take(T, e, 4, w.E.re, c); tab_take(T, e, 5, w.E.im, c); tab_take(T, e, 6, w.F.re, c); tab_take(T, e, 7, w.F.im, c);
@@ -133,25 +133,16 @@ FQ_FN ptR1 dh_loop_windowed(const TabView& T, DhState& D) {
   return loop_windowed(D.plan, sel);
 }
 
-// fixed base: the table is read-only, shared by all threads (constant bank), 8 entries x 32 words
-struct SelectConst {
-  const u32* tab;   // [8][32], entry layout N.re N.im D.re D.im E.re E.im F.re F.im
+// fixed base (the reference's table_windowed / table_endo shape): ONE table of 8 entries x 8 quads shared by all threads
+// of a CTA, held in shared memory as [entry][quad] (stride 1).  Every thread reads the same address (broadcast), entry 7 is
+// loaded unconditionally and entries 0..6 under the digit's predicate, exactly like tab_select.
+struct SelectBroadcast {
+  TabView T;
   FQ_MFN ptR2 operator()(u32 idx) const {
-    u32 w[32];
+    ptR2 S = tab_load(T, 7);
     FQ_UNROLL
-    for (int j = 0; j < 32; j++) w[j] = tab[7 * 32 + j];
-    FQ_UNROLL
-    for (int e = 0; e < 7; e++) {
-      const bool c = idx == (u32)e;
-      FQ_UNROLL
-      for (int j = 0; j < 32; j++) w[j] = c ? tab[e * 32 + j] : w[j];
-    }
-    ptR2 P;
-    P.N = fp2_set(fp_set(w[0], w[1], w[2], w[3]), fp_set(w[4], w[5], w[6], w[7]));
-    P.D = fp2_set(fp_set(w[8], w[9], w[10], w[11]), fp_set(w[12], w[13], w[14], w[15]));
-    P.E = fp2_set(fp_set(w[16], w[17], w[18], w[19]), fp_set(w[20], w[21], w[22], w[23]));
-    P.F = fp2_set(fp_set(w[24], w[25], w[26], w[27]), fp_set(w[28], w[29], w[30], w[31]));
-    return P;
+    for (int e = 0; e < 7; e++) tab_take_r2(T, e, S, idx == (u32)e);
+    return S;
   }
 };
 FQ_FN void r2_to_words(const ptR2& P, u32* w) {
@@ -160,9 +151,9 @@ FQ_FN void r2_to_words(const ptR2& P, u32* w) {
   for (int q = 0; q < 8; q++) { FQ_UNROLL for (int j = 0; j < 4; j++) w[q * 4 + j] = f[q]->v[j]; }
 }
 
-// [k]B for the base point whose table is `tab`; returns canonical affine.  MUL_windowed(k, ., table) + R1toAffine.
-FQ_FN void mul_fixed_base(const scal& k, const u32* tab, fp2& ox, fp2& oy) {
-  SelectConst sel; sel.tab = tab;
+// [k]B for the base point whose table is T; returns canonical affine.  MUL_windowed(k, ., table) + R1toAffine.
+FQ_FN void mul_fixed_base(const scal& k, const TabView& T, fp2& ox, fp2& oy) {
+  SelectBroadcast sel; sel.T = T;
   ptR1 R = mul_windowed(k, sel);
   pt_to_affine(R, ox, oy);
 }

@@ -33,14 +33,21 @@ __global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_
   st8(enc, row, wo);
 }
 
-// fixed base: [k]G (DH = false) or [k][392]G with neutral rejection (DH = true); table in the constant bank
+// fixed base: [k]G (DH = false) or [k][392]G with neutral rejection (DH = true).  The CTA copies the 1 KiB table of its base
+// point from the constant bank into shared memory once; the selection then reads it by broadcast (dh.cuh SelectBroadcast).
 template <bool DH, bool ENDO> __global__ void __launch_bounds__(256)
 k_fixed_base(const void* k, void* out, unsigned char* status, size_t n) {
+  __shared__ uint4 stab[64];
+  if (threadIdx.x < 64) {
+    const u32* src = c_base_tabs + (ENDO ? 512 : 0) + (DH ? 256 : 0) + 4 * threadIdx.x;
+    stab[threadIdx.x] = make_uint4(src[0], src[1], src[2], src[3]);
+  }
+  __syncthreads();
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   u32 wk[8], wo[8];
   ld8(k, row, wk);
-  u32 st = row_fixed_base<DH, ENDO>(wk, c_base_tabs + (ENDO ? 512 : 0) + (DH ? 256 : 0), wo);
+  u32 st = row_fixed_base<DH, ENDO>(wk, stab, wo);
   if (status) status[row] = (unsigned char)st;
   st8(out, row, wo);
 }

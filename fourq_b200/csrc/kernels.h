@@ -22,6 +22,7 @@ cudaError_t fqk_dh_endo(int affine, const void* k, const void* pt, void* out, vo
 cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s);
 // fixed-base per-digit tables (kernels_comb.cu): tabs is the device buffer returned by fqk_comb_init
 cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s);
-cudaError_t fqk_comb(int dh, const void* tabs, const void* k, void* out, void* status, size_t n, int sms, cudaStream_t s);
+size_t fqk_comb_scratch_bytes(size_t n);     // device scratch the caller passes to fqk_comb
+cudaError_t fqk_comb(int dh, const void* tabs, const void* k, void* out, void* status, size_t n, void* scratch, int sms, cudaStream_t s);
 cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s);

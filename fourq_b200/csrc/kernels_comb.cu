@@ -1,8 +1,8 @@
 // kernels_comb.cu -- fixed-base kernels on per-digit tables (comb.cuh): fq_mul_base_comb, fq_dh_base_comb.
 // One thread = one row; the 47.25 KiB table of the base point is copied once per CTA from global to shared memory and
-// then read with warp-uniform addresses (broadcast), so the per-thread state is registers only.
-#include "kernels.h"
-#include "kio.cuh"
+// then read with warp-uniform addresses (broadcast), so the per-thread state is registers only.  k_comb leaves the result
+// projective; k_dh_finish (kernels_dh.cuh) normalises four rows per inversion and encodes.
+#include "kernels_dh.cuh"
 #include "comb.cuh"
 
 #define FQ_COMB_THREADS 256
@@ -15,8 +15,9 @@ __global__ void __launch_bounds__(64) k_comb_build(u32* tabs) {
   comb_build_digit(which, i, tabs + which * FQ_COMB_WORDS + i * FQ_COMB_DIGIT_WORDS);
 }
 
+// [k]B in R1 for every row; (X, Y, Z) go to scratch for k_dh_finish (one inversion per FQ_FIN_ROWS rows, encode)
 template <bool DH> __global__ void __launch_bounds__(FQ_COMB_THREADS)
-k_comb(const u32* __restrict__ tabs, const void* __restrict__ k, void* __restrict__ out, unsigned char* __restrict__ status, size_t n) {
+k_comb(const u32* __restrict__ tabs, const void* __restrict__ k, DhScratch sc, size_t n) {
   extern __shared__ uint4 stab4[];
   const uint4* src = reinterpret_cast<const uint4*>(tabs + (DH ? FQ_COMB_WORDS : 0));
   for (int j = threadIdx.x; j < FQ_COMB_WORDS / 4; j += FQ_COMB_THREADS) stab4[j] = src[j];
@@ -26,11 +27,16 @@ k_comb(const u32* __restrict__ tabs, const void* __restrict__ k, void* __restric
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     size_t row = tile * FQ_COMB_THREADS + threadIdx.x;
     if (row >= n) continue;
-    u32 wk[8], wo[8];
+    u32 wk[8];
     ld8(k, row, wk);
-    u32 st = row_comb<DH>(wk, stab, wo);
-    if (status) status[row] = (unsigned char)st;
-    st8(out, row, wo);
+    scal sk;
+    FQ_UNROLL
+    for (int i = 0; i < 8; i++) sk.v[i] = wk[i];
+    ptR1 R = mul_comb(sk, stab);
+    uint4* o = sc.R + row;
+    stq(o, R.X.re); stq(o + sc.npad, R.X.im); stq(o + 2 * sc.npad, R.Y.re); stq(o + 3 * sc.npad, R.Y.im);
+    stq(o + 4 * sc.npad, R.Z.re); stq(o + 5 * sc.npad, R.Z.im);
+    sc.meta[row] = 0;
   }
 }
 
@@ -47,13 +53,27 @@ cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s) {
   return cudaSuccess;
 }
 
-cudaError_t fqk_comb(int dh, const void* tabs, const void* k, void* out, void* status, size_t n, int sms, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  // persistent CTAs: the table copy (47 KiB) is paid once per CTA, each CTA then walks over tiles of 256 rows
-  unsigned tiles = grid_for(n, FQ_COMB_THREADS);
-  unsigned cap = (unsigned)sms * 4u;
-  unsigned g = tiles < cap ? tiles : cap;
-  if (dh) k_comb<true><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, k, out, (unsigned char*)status, n);
-  else k_comb<false><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, k, out, (unsigned char*)status, n);
-  return cudaGetLastError();
+size_t fqk_comb_scratch_bytes(size_t n) { return fin_scratch_bytes(n < FQ_DH_MAX_BATCH ? n : FQ_DH_MAX_BATCH); }
+
+cudaError_t fqk_comb(int dh, const void* tabs, const void* k, void* out, void* status, size_t n, void* scratch, int sms, cudaStream_t s) {
+  for (size_t r0 = 0; r0 < n; r0 += FQ_DH_MAX_BATCH) {
+    const size_t rows = n - r0 < FQ_DH_MAX_BATCH ? n - r0 : FQ_DH_MAX_BATCH;
+    DhScratch sc = fin_scratch_view(scratch, rows);
+    // persistent CTAs: the table copy (47 KiB) is paid once per CTA, each CTA then walks over tiles of 256 rows
+    unsigned tiles = grid_for(rows, FQ_COMB_THREADS);
+    unsigned cap = (unsigned)sms * 4u;
+    unsigned g = tiles < cap ? tiles : cap;
+    const char* kk = (const char*)k + 32 * r0; char* oo = (char*)out + 32 * r0;
+    unsigned char* st = status ? (unsigned char*)status + r0 : nullptr;
+    if (dh) {
+      k_comb<true><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
+      k_dh_finish<false, true><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    } else {
+      k_comb<false><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
+      k_dh_finish<false, false><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }

@@ -112,7 +112,9 @@ k_dh_ladder(DhScratch sc) {
 // (curve4q.py:459), encode (curve4q.py:41-46).  Thread t owns rows t, t + stride, ...  Z is never 0 on the curve (complete
 // formulas); a zero (only possible on rows that already failed validation) is replaced by 1 so it cannot poison the
 // shared product.
-template <bool AFFINE> __global__ void __launch_bounds__(FQ_DH_THREADS)
+// CHECK_NEUTRAL = false (fq_mul_base_comb): MUL_* has no failure path, the neutral point is encoded like any other and
+// status may be null.
+template <bool AFFINE, bool CHECK_NEUTRAL> __global__ void __launch_bounds__(FQ_DH_THREADS)
 k_dh_finish(DhScratch sc, void* __restrict__ out, unsigned char* __restrict__ status, size_t n) {
   const size_t stride = (size_t)gridDim.x * FQ_DH_THREADS;
   const size_t t = (size_t)blockIdx.x * FQ_DH_THREADS + threadIdx.x;
@@ -144,14 +146,28 @@ k_dh_finish(DhScratch sc, void* __restrict__ out, unsigned char* __restrict__ st
     if (row < n) {
       u32 st = sc.meta[row] >> 8;
       const bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());      // curve4q.py:459
-      if (st == FQ_ST_OK && neutral) st = FQ_ST_NEUTRAL;
+      if (CHECK_NEUTRAL && st == FQ_ST_OK && neutral) st = FQ_ST_NEUTRAL;
       u32 wo[AFFINE ? 16 : 8];
       if (AFFINE) { if (st == FQ_ST_OK) { row_store_fp2(wo, ox); row_store_fp2(wo + 8, oy); } else row_zero(wo, 16); }
       else { if (st == FQ_ST_OK) pt_encode(ox, oy, wo); else row_zero(wo, 8); }
-      status[row] = (unsigned char)st;
+      if (status) status[row] = (unsigned char)st;
       if (AFFINE) { st8(out, 2 * row, wo); st8(out, 2 * row + 1, wo + 8); } else st8(out, row, wo);
     }
   }
+}
+static inline unsigned dh_finish_grid(size_t rows) {
+  return (unsigned)((((rows + FQ_FIN_ROWS - 1) / FQ_FIN_ROWS) + FQ_DH_THREADS - 1) / FQ_DH_THREADS);
+}
+// scratch of a producer that only hands (X, Y, Z) and a status word to k_dh_finish (the fixed-base comb kernel)
+static inline size_t fin_scratch_bytes(size_t rows) {
+  size_t npad = (rows + 255) / 256 * 256;
+  return npad * (6 * 16 + 4);
+}
+static inline DhScratch fin_scratch_view(void* base, size_t rows) {
+  DhScratch sc;
+  sc.npad = (rows + 255) / 256 * 256;
+  sc.tab = nullptr; sc.plan = nullptr; sc.R = reinterpret_cast<uint4*>(base); sc.meta = reinterpret_cast<u32*>(sc.R + 6 * sc.npad);
+  return sc;
 }
 
 template <bool ENDO> static cudaError_t dh_init() {
@@ -166,7 +182,7 @@ template <bool ENDO> static cudaError_t dh_launch(int affine, const void* k, con
     const size_t rows = n - r0 < FQ_DH_MAX_BATCH ? n - r0 : FQ_DH_MAX_BATCH;
     DhScratch sc = dh_scratch_view(scratch, rows);
     const unsigned g = (unsigned)(sc.npad / FQ_DH_THREADS);
-    const unsigned gf = (unsigned)((((rows + FQ_FIN_ROWS - 1) / FQ_FIN_ROWS) + FQ_DH_THREADS - 1) / FQ_DH_THREADS);
+    const unsigned gf = dh_finish_grid(rows);
     const char* kk = (const char*)k + 32 * r0; const char* pp = (const char*)pt + in_pt * r0;
     char* oo = (char*)out + out_b * r0; unsigned char* st = (unsigned char*)status + r0;
     if (ev) cudaEventRecord(ev[0], s);
@@ -175,8 +191,8 @@ template <bool ENDO> static cudaError_t dh_launch(int affine, const void* k, con
     if (ev) cudaEventRecord(ev[1], s);
     k_dh_ladder<ENDO><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(sc);
     if (ev) cudaEventRecord(ev[2], s);
-    if (affine) k_dh_finish<true><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
-    else k_dh_finish<false><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    if (affine) k_dh_finish<true, true><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    else k_dh_finish<false, true><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
     if (ev) cudaEventRecord(ev[3], s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -87,10 +87,12 @@ template <bool ENDO> FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* o
   return row_dh_finish<true>(st, row_dh_loop<ENDO>(T, D), out);
 }
 // fq_mul_base (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base (true): encode([k][392]G) with the neutral check
-template <bool CHECK_NEUTRAL, bool ENDO> FQ_FN u32 row_fixed_base(const u32* k, const u32* tab, u32* out) {
+// tab: the 64 quads of the base point's table, [entry][quad], in shared memory on the device
+template <bool CHECK_NEUTRAL, bool ENDO> FQ_FN u32 row_fixed_base(const u32* k, uint4* tab, u32* out) {
   fp2 ox, oy;
-  if (ENDO) { SelectConst sel; sel.tab = tab; pt_to_affine(mul_endo(row_load_scalar(k), sel), ox, oy); }
-  else mul_fixed_base(row_load_scalar(k), tab, ox, oy);
+  TabView T; T.base = tab; T.stride = 1;
+  if (ENDO) { SelectBroadcast sel; sel.T = T; pt_to_affine(mul_endo(row_load_scalar(k), sel), ox, oy); }
+  else mul_fixed_base(row_load_scalar(k), T, ox, oy);
   u32 st = FQ_ST_OK;
   if (CHECK_NEUTRAL && (fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one()))) st = FQ_ST_NEUTRAL;
   if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);

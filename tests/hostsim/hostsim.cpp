@@ -91,8 +91,8 @@ int sim_fixed_base(int dh, const uint8_t* k, uint8_t* out, uint8_t* status, size
   const int endo = dh >> 1; dh &= 1;
   for (size_t i = 0; i < n; i++) {
     u32 wk[8], wo[8]; memcpy(wk, k + 32 * i, 32);
-    u32 st = endo ? (dh ? row_fixed_base<true, true>(wk, g_tabs + 768, wo) : row_fixed_base<false, true>(wk, g_tabs + 512, wo))
-                  : (dh ? row_fixed_base<true, false>(wk, g_tabs + 256, wo) : row_fixed_base<false, false>(wk, g_tabs, wo));
+    u32 st = endo ? (dh ? row_fixed_base<true, true>(wk, (uint4*)(g_tabs + 768), wo) : row_fixed_base<false, true>(wk, (uint4*)(g_tabs + 512), wo))
+                  : (dh ? row_fixed_base<true, false>(wk, (uint4*)(g_tabs + 256), wo) : row_fixed_base<false, false>(wk, (uint4*)g_tabs, wo));
     if (status) status[i] = (uint8_t)st;
     memcpy(out + 32 * i, wo, 32);
   }

@@ -9,6 +9,7 @@ Every measured batch is spot-checked bit-for-bit against the oracle (first rows)
 
 cfg 2  GF(p^2) field microbench: 2^26 mul / sqr (HBM-bound: 96 / 64 B per element), 2^20 inv (multiplier-bound)
 cfg 4  fixed-base keygen: 2^24 scalars x G, per-digit tables ("comb") vs MUL_windowed / MUL_endo with a table, N GPUs
+       (comb: 62 mixed additions x 336 multiply-adds + one inversion per 4 rows (1,504 / 4) + 5 GF(p^2) multiplications)
 cfg 5  compare.py analogue: X25519 ladder vs Curve4Q DH, 2^20 rows each
 """
 import argparse
@@ -82,7 +83,7 @@ def main():
     k = np.random.default_rng(5).integers(0, 256, (n, 32), np.uint8)
     dk = fqdev.DeviceBuffer.from_host(dev, k); do = fqdev.DeviceBuffer(dev, n * 32)
     ref = None
-    for alg, op, imads in (("comb", "mul_base_comb", 20832 + 1504 + 96), ("endo", "mul_endo_base", 64 * 656 + 1504 + 96), ("windowed", "mul_base", 92624)):
+    for alg, op, imads in (("comb", "mul_base_comb", 20832 + 1504 // 4 + 5 * 48), ("endo", "mul_endo_base", 64 * 656 + 1504 + 96), ("windowed", "mul_base", 92624)):
         ms = kernel_ms(op, dev, dk, None, do, None, n, reps=3)
         got = do.to_host((n, 32))
         if ref is None:
