@@ -105,6 +105,13 @@ size_t dh_chunk_rows() {
   return v;
 }
 
+// FQ_PIPELINE_RAMP=0 disables the ramped chunk schedule of run_host (all chunks full size)
+bool ramp_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FQ_PIPELINE_RAMP"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 OpDesc describe(int op) {
   switch (op) {
     case FQ_DEVOP_FP2_MUL: case FQ_DEVOP_FP2_ADD: case FQ_DEVOP_FP2_SUB: return {op, 32, 32, 32, false, (size_t)1 << 20};
@@ -165,14 +172,31 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* 
 
   size_t per = (n + ndev - 1) / ndev;
   std::vector<ChunkEv> evs;
-  size_t max_chunks = (per + d.chunk_rows - 1) / d.chunk_rows;
+  // Chunk schedule of one slice (the same for every device): ramp up from chunk/8 so that the first kernels start after
+  // a short copy, full chunks in the middle, ramp down so that little work and a short copy-back remain exposed at the
+  // end.  Small batches (<= one chunk) are not split.
+  std::vector<size_t> bounds;                        // chunk c covers [bounds[c], bounds[c+1]) of the slice
+  {
+    const size_t full = d.chunk_rows, small = full / 8 >= 4096 ? full / 8 : full;
+    size_t pos = 0, sz = (per > full && ramp_enabled()) ? small : full;
+    bounds.push_back(0);
+    while (pos < per) {
+      size_t left = per - pos;
+      size_t take = sz < left ? sz : left;
+      if (ramp_enabled() && per > full && left > small && left <= 2 * take) take = (left / 2 + 127) / 128 * 128;   // ramp down by halves
+      pos += take; bounds.push_back(pos);
+      if (sz < full) sz = sz * 2 < full ? sz * 2 : full;
+    }
+  }
+  size_t max_chunks = bounds.size() - 1;
   int rc = FQ_OK;
   for (size_t c = 0; c < max_chunks && rc == FQ_OK; c++) {
     for (int i = 0; i < ndev && rc == FQ_OK; i++) {
       size_t lo = (size_t)i * per, hi = lo + per < n ? lo + per : n;
-      size_t r0 = lo + c * d.chunk_rows;
+      size_t r0 = lo + bounds[c];
       if (lo >= n || r0 >= hi) continue;
-      size_t rows = hi - r0 < d.chunk_rows ? hi - r0 : d.chunk_rows;
+      size_t r1 = lo + bounds[c + 1] < hi ? lo + bounds[c + 1] : hi;
+      size_t rows = r1 - r0;
       int dev = g_dev_base + i;
       if ((rc = ctx_init(dev)) != FQ_OK) break;
       DevCtx& cx = g_ctx[dev];
