@@ -117,6 +117,9 @@ OpDesc describe(int op) {
     case FQ_DEVOP_FP2_MUL: case FQ_DEVOP_FP2_ADD: case FQ_DEVOP_FP2_SUB: return {op, 32, 32, 32, false, (size_t)1 << 20};
     case FQ_DEVOP_FP2_SQR: case FQ_DEVOP_FP2_NEG: case FQ_DEVOP_FP2_CONJ: return {op, 32, 0, 32, false, (size_t)1 << 20};
     case FQ_DEVOP_FP2_INV: return {op, 32, 0, 32, false, (size_t)1 << 18};
+    case FQ_DEVOP_FP_BASE + FQ_FP_MUL: case FQ_DEVOP_FP_BASE + FQ_FP_ADD: case FQ_DEVOP_FP_BASE + FQ_FP_SUB: return {op, 16, 16, 16, false, (size_t)1 << 20};
+    case FQ_DEVOP_FP_BASE + FQ_FP_SQR: case FQ_DEVOP_FP_BASE + FQ_FP_NEG: return {op, 16, 0, 16, false, (size_t)1 << 20};
+    case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT: return {op, 16, 0, 16, false, (size_t)1 << 18};
     case FQ_DEVOP_DECODE: return {op, 32, 0, 64, true, (size_t)1 << 18};
     case FQ_DEVOP_ENCODE: return {op, 64, 0, 32, false, (size_t)1 << 20};
     case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, 32, 32, 32, true, dh_chunk_rows()};
@@ -142,6 +145,9 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_FP2_SUB: return fqk_fp2_op(FQK_SUB, a, b, out, n, s);
     case FQ_DEVOP_FP2_NEG: return fqk_fp2_op(FQK_NEG, a, b, out, n, s);
     case FQ_DEVOP_FP2_CONJ: return fqk_fp2_op(FQK_CONJ, a, b, out, n, s);
+    case FQ_DEVOP_FP_BASE + FQ_FP_MUL: case FQ_DEVOP_FP_BASE + FQ_FP_SQR: case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_ADD:
+    case FQ_DEVOP_FP_BASE + FQ_FP_SUB: case FQ_DEVOP_FP_BASE + FQ_FP_NEG: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT:
+      return fqk_fp_op(op - FQ_DEVOP_FP_BASE, a, b, out, n, s);
     case FQ_DEVOP_DECODE: return fqk_decode(a, out, status, n, s);
     case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
     case FQ_DEVOP_DH: return fqk_dh(0, 0, a, b, out, status, n, cx.dh_scratch[si], s, ev);
@@ -265,6 +271,10 @@ int fq_fp2_add(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int n
 int fq_fp2_sub(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SUB, a, b, out, nullptr, n, ndev); }
 int fq_fp2_neg(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_NEG, a, nullptr, out, nullptr, n, ndev); }
 int fq_fp2_conj(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_CONJ, a, nullptr, out, nullptr, n, ndev); }
+int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) {
+  if (op < FQ_FP_MUL || op > FQ_FP_INVSQRT) return fail(FQ_ERR_ARG, "unknown GF(p) operation %d", op);
+  return run_host(FQ_DEVOP_FP_BASE + op, a, b, out, nullptr, n, ndev);
+}
 int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE, enc, nullptr, xy, status, n, ndev); }
 int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev) { return run_host(FQ_DEVOP_ENCODE, xy, nullptr, enc, nullptr, n, ndev); }
 int fq_dh(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH, k, enc_pt, enc_out, status, n, ndev); }

@@ -15,6 +15,17 @@ template <int OP> __global__ void __launch_bounds__(256) k_fp2_op(const void* a,
   st8(out, row, wo);
 }
 
+// GF(p) op on 16-byte rows: one 128-bit load per operand and one 128-bit store per thread
+template <int OP> __global__ void __launch_bounds__(256) k_fp_op(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  uint4 va = a[row], vb = make_uint4(0, 0, 0, 0);
+  if (OP == FQ_FPOP_MUL || OP == FQ_FPOP_ADD || OP == FQ_FPOP_SUB) vb = b[row];
+  u32 wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w}, wo[4];
+  row_fp_op<OP>(wa, wb, wo);
+  out[row] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+}
+
 __global__ void __launch_bounds__(256) k_decode(const void* enc, void* xy, unsigned char* status, size_t n) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
@@ -105,6 +116,22 @@ cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n
     case FQK_SUB: k_fp2_op<FQ_OP_SUB><<<g, 256, 0, s>>>(a, b, out, n); break;
     case FQK_NEG: k_fp2_op<FQ_OP_NEG><<<g, 256, 0, s>>>(a, b, out, n); break;
     case FQK_CONJ: k_fp2_op<FQ_OP_CONJ><<<g, 256, 0, s>>>(a, b, out, n); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t fqk_fp_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  unsigned g = grid_for(n, 256);
+  const uint4* A = (const uint4*)a; const uint4* B = (const uint4*)b; uint4* O = (uint4*)out;
+  switch (op) {
+    case FQ_FPOP_MUL: k_fp_op<FQ_FPOP_MUL><<<g, 256, 0, s>>>(A, B, O, n); break;
+    case FQ_FPOP_SQR: k_fp_op<FQ_FPOP_SQR><<<g, 256, 0, s>>>(A, B, O, n); break;
+    case FQ_FPOP_INV: k_fp_op<FQ_FPOP_INV><<<g, 256, 0, s>>>(A, B, O, n); break;
+    case FQ_FPOP_ADD: k_fp_op<FQ_FPOP_ADD><<<g, 256, 0, s>>>(A, B, O, n); break;
+    case FQ_FPOP_SUB: k_fp_op<FQ_FPOP_SUB><<<g, 256, 0, s>>>(A, B, O, n); break;
+    case FQ_FPOP_NEG: k_fp_op<FQ_FPOP_NEG><<<g, 256, 0, s>>>(A, B, O, n); break;
+    case FQ_FPOP_INVSQRT: k_fp_op<FQ_FPOP_INVSQRT><<<g, 256, 0, s>>>(A, B, O, n); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -35,6 +35,23 @@ template <int OP> FQ_FN void row_fp2_op(const u32* a, const u32* b, u32* out) {
   row_store_fp2(out, r);
 }
 
+// GF(p) ops on 16-byte rows (fields.py:29-122 GFp.add/sub/mul/sqr/neg/inv/invsqrt): any 128-bit input (the reference reduces
+// ints mod p), canonical output
+enum { FQ_FPOP_MUL = 0, FQ_FPOP_SQR = 1, FQ_FPOP_INV = 2, FQ_FPOP_ADD = 3, FQ_FPOP_SUB = 4, FQ_FPOP_NEG = 5, FQ_FPOP_INVSQRT = 6 };
+template <int OP> FQ_FN void row_fp_op(const u32* a, const u32* b, u32* out) {
+  fp x = fp_from_u128(fp_set(a[0], a[1], a[2], a[3])), r;
+  if (OP == FQ_FPOP_MUL) r = fp_mul(x, fp_from_u128(fp_set(b[0], b[1], b[2], b[3])));
+  else if (OP == FQ_FPOP_ADD) r = fp_add(x, fp_from_u128(fp_set(b[0], b[1], b[2], b[3])));
+  else if (OP == FQ_FPOP_SUB) r = fp_sub(x, fp_from_u128(fp_set(b[0], b[1], b[2], b[3])));
+  else if (OP == FQ_FPOP_SQR) r = fp_sqr(x);
+  else if (OP == FQ_FPOP_INV) r = fp_inv(x);
+  else if (OP == FQ_FPOP_NEG) r = fp_neg(x);
+  else r = fp_invsqrt(x);
+  r = fp_canon(r);
+  FQ_UNROLL
+  for (int i = 0; i < 4; i++) out[i] = r.v[i];
+}
+
 // decode: 8 words -> 16 words (x0|x1|y0|y1), zero-filled on failure
 FQ_FN u32 row_decode(const u32* enc, u32* xy) {
   fp2 x, y;

@@ -6,6 +6,7 @@
     DH_windowed(m, P) -> affine Q      :464-465     DH_windowed(k[N,32], XY[N,64]) -> (XY[N,64], status[N])
     DH_endo(m, P) -> affine Q          :467-468     DH_endo(k[N,32], XY[N,64]) -> (XY[N,64], status[N])
     encode(DH_*(m, decode(B)))                      DH(k[N,32], B[N,32], algorithm=) -> (B[N,32], status[N])
+    y of DH_*(m, decode(B))  (draft :707-714)       DH(k, B, y_only=True) -> (y[N,32], status[N])
     DH_*(m, G, table=T392)             :743-762     DH_base(k[N,32], algorithm=) -> (B[N,32], status[N])
     MUL_*(m, G, table=T) -> [m]G       :582-584     MUL_base(k[N,32], algorithm=) -> B[N,32]
 
@@ -91,7 +92,9 @@ def decode(B, ndev=1, strict=False, out=None, status=None):
     return XY, status
 
 
-def DH(k, B, ndev=1, strict=False, out=None, status=None, algorithm=None):
+def DH(k, B, ndev=1, strict=False, out=None, status=None, algorithm=None, y_only=False):
+    """encode(DH_*(k, decode(B))).  y_only=True returns the draft's shared secret instead: the y coordinate of the shared
+    point as a 32-byte string (draft-ladd-cfrg-4q.md:707-714), i.e. the encoding with the sign bit of x cleared."""
     k = _lib.rows(k, 32, "k")
     B = _lib.rows(B, 32, "B")
     if k.shape[0] != B.shape[0]:
@@ -101,6 +104,8 @@ def DH(k, B, ndev=1, strict=False, out=None, status=None, algorithm=None):
     status = _buf(status, (n,), "status")
     fn = _lib.lib().fq_dh_endo if _alg(algorithm) == "endo" else _lib.lib().fq_dh
     _lib.check(fn(_lib.ptr(k), _lib.ptr(B), _lib.ptr(out), _lib.ptr(status), n, ndev))
+    if y_only:
+        out[:, 31] &= 0x7F
     if strict:
         _raise_first(status)
     return out, status

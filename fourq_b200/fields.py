@@ -63,6 +63,55 @@ class GFp2:
         return np.where(c, _lib.rows(x, 32, "x"), _lib.rows(y, 32, "y"))
 
 
+def _fp(op, a, b, ndev):
+    a = _lib.rows(a, 16, "a")
+    if b is not None:
+        b = _lib.rows(b, 16, "b")
+        if a.shape != b.shape:
+            raise ValueError("operands must have the same shape")
+    out = np.empty_like(a)
+    _lib.check(_lib.lib().fq_fp_op(_lib.FPOP[op], _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], ndev))
+    return out
+
+
+class GFp:
+    """Static methods named after fields.py GFp.*; an element is a 16-byte little-endian row (fields.py:125-126), arrays are
+    (N, 16) uint8.  Any 128-bit input is accepted (the reference reduces ints mod p), results are canonical."""
+
+    @staticmethod
+    def add(x, y, ndev=1):       # fields.py:30-33
+        return _fp("add", x, y, ndev)
+
+    @staticmethod
+    def sub(x, y, ndev=1):       # fields.py:36-39
+        return _fp("sub", x, y, ndev)
+
+    @staticmethod
+    def mul(x, y, ndev=1):       # fields.py:42-45
+        return _fp("mul", x, y, ndev)
+
+    @staticmethod
+    def sqr(x, ndev=1):          # fields.py:48-51
+        return _fp("sqr", x, None, ndev)
+
+    @staticmethod
+    def neg(x, ndev=1):          # fields.py:54-57
+        return _fp("neg", x, None, ndev)
+
+    @staticmethod
+    def inv(x, ndev=1):          # fields.py:67-106
+        return _fp("inv", x, None, ndev)
+
+    @staticmethod
+    def invsqrt(x, ndev=1):      # fields.py:110-122
+        return _fp("invsqrt", x, None, ndev)
+
+    @staticmethod
+    def select(c, x, y):         # fields.py:60-64; c is a (N,) 0/1 array.  Pure data movement, done by numpy.
+        c = np.asarray(c).astype(bool).reshape(-1, 1)
+        return np.where(c, _lib.rows(x, 16, "x"), _lib.rows(y, 16, "y"))
+
+
 def pack(pairs):
     """[(re, im), ...] Python ints -> (N, 32) uint8 rows (fields.py:125-126 packing of each half)."""
     out = np.empty((len(pairs), 32), np.uint8)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 102
+#define FQ_VERSION 103
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -65,6 +65,18 @@ FQ_API int fq_fp2_add(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n
 FQ_API int fq_fp2_sub(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
 FQ_API int fq_fp2_neg(const uint8_t* a, uint8_t* out, size_t n, int ndev);
 FQ_API int fq_fp2_conj(const uint8_t* a, uint8_t* out, size_t n, int ndev);
+
+/* ---- GF(p) field ops on 16-byte rows (little-endian 128-bit values): fields.py GFp.mul :42, sqr :48, inv :67-106,
+ * add :30, sub :36, neg :54, invsqrt :110-122.  a, b, out are (n,16); b is ignored by the unary ops (may be NULL).  Inputs may
+ * be any 128-bit value (the reference reduces ints mod p); outputs are canonical. */
+#define FQ_FP_MUL 0
+#define FQ_FP_SQR 1
+#define FQ_FP_INV 2
+#define FQ_FP_ADD 3
+#define FQ_FP_SUB 4
+#define FQ_FP_NEG 5
+#define FQ_FP_INVSQRT 6
+FQ_API int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
 
 /* ---- point codec: curve4q.py decode :49-96 (enc (n,32) -> xy (n,64) + status), encode :41-46 (xy -> enc).
  * Unlike the reference, decode does not modify its input. */
@@ -113,6 +125,7 @@ FQ_API int fq_host_free(void* p);
 #define FQ_DEVOP_FP2_SUB 4
 #define FQ_DEVOP_FP2_NEG 5
 #define FQ_DEVOP_FP2_CONJ 6
+#define FQ_DEVOP_FP_BASE 32    /* FQ_DEVOP_FP_BASE + FQ_FP_*: GF(p) ops on 16-byte rows, a (, b), out */
 #define FQ_DEVOP_DECODE 16     /* a = enc, out = xy, status */
 #define FQ_DEVOP_ENCODE 17     /* a = xy, out = enc */
 #define FQ_DEVOP_DH 18         /* a = k, b = enc_pt, out, status */

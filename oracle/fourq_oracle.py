@@ -614,6 +614,29 @@ def row_fp2(op, a, b=None):
     raise ValueError(op)
 
 
+def row_fp(op, a, b=None):
+    """GF(p) op on 16-byte little-endian rows; inputs are arbitrary 128-bit ints as in the reference (fields.py:29-122)."""
+    x = int.from_bytes(a, "little")
+    y = int.from_bytes(b, "little") if b is not None else None
+    if op == "add":
+        r = fp_add(x, y)
+    elif op == "sub":
+        r = fp_sub(x, y)
+    elif op == "mul":
+        r = fp_mul(x, y)
+    elif op == "sqr":
+        r = fp_sqr(x)
+    elif op == "neg":
+        r = fp_neg(x % P127) % P127
+    elif op == "inv":
+        r = fp_inv(x % P127)
+    elif op == "invsqrt":
+        r = fp_invsqrt(x % P127)
+    else:
+        raise ValueError(op)
+    return fp_to_le(r)
+
+
 # ------------------------------------------------------------------ X25519 (curve25519.py:17-91)
 
 

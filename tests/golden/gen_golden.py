@@ -126,6 +126,24 @@ def main():
         fld["fp_invsqrt"].append([le16(xr).hex(), le16(GFp.invsqrt(xr)).hex()])
     dump("fields.json", fld)
 
+    # ------------------------------------------------------------------ GF(p) ops on 16-byte rows (fields.py:29-122)
+    rng = random.Random(0xF9127)
+    fp_inputs = [(a, b) for a in edge for b in edge[:8]]
+    fp_inputs += [(rng.getrandbits(128), rng.getrandbits(128)) for _ in range(96)]
+    fp_inputs += [(rng.getrandbits(127), rng.getrandbits(127)) for _ in range(64)]
+    fpv = {"add": [], "sub": [], "mul": [], "sqr": [], "neg": [], "inv": [], "invsqrt": []}
+    for i, (a, b) in enumerate(fp_inputs):
+        fpv["add"].append([le16(a).hex(), le16(b).hex(), le16(GFp.add(a, b)).hex()])
+        fpv["sub"].append([le16(a).hex(), le16(b).hex(), le16(GFp.sub(a, b)).hex()])
+        fpv["mul"].append([le16(a).hex(), le16(b).hex(), le16(GFp.mul(a, b)).hex()])
+        fpv["sqr"].append([le16(a).hex(), le16(GFp.sqr(a)).hex()])
+        ar = a % p                              # neg / inv / invsqrt: reduced input, as the reference's callers pass
+        fpv["neg"].append([le16(ar).hex(), le16(GFp.neg(ar) % p).hex()])
+        if i % 3 == 0:
+            fpv["inv"].append([le16(ar).hex(), le16(GFp.inv(ar)).hex()])
+            fpv["invsqrt"].append([le16(ar).hex(), le16(GFp.invsqrt(ar)).hex()])
+    dump("fp.json", fpv)
+
     # ------------------------------------------------------------------ points used below
     def mulG(m):
         return c4q.R1toAffine(c4q.MUL_windowed(m, G_R1, table=T_G))

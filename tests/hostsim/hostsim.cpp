@@ -40,6 +40,27 @@ int sim_fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t 
   return 0;
 }
 
+// GF(p) ops of the fq_fp_op entry point: op = FQ_FPOP_*, 16-byte rows
+int sim_fp_row_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wa[4], wb[4] = {0, 0, 0, 0}, wo[4];
+    memcpy(wa, a + 16 * i, 16);
+    if (b) memcpy(wb, b + 16 * i, 16);
+    switch (op) {
+      case FQ_FPOP_MUL: row_fp_op<FQ_FPOP_MUL>(wa, wb, wo); break;
+      case FQ_FPOP_SQR: row_fp_op<FQ_FPOP_SQR>(wa, wb, wo); break;
+      case FQ_FPOP_INV: row_fp_op<FQ_FPOP_INV>(wa, wb, wo); break;
+      case FQ_FPOP_ADD: row_fp_op<FQ_FPOP_ADD>(wa, wb, wo); break;
+      case FQ_FPOP_SUB: row_fp_op<FQ_FPOP_SUB>(wa, wb, wo); break;
+      case FQ_FPOP_NEG: row_fp_op<FQ_FPOP_NEG>(wa, wb, wo); break;
+      case FQ_FPOP_INVSQRT: row_fp_op<FQ_FPOP_INVSQRT>(wa, wb, wo); break;
+      default: return -1;
+    }
+    memcpy(out + 16 * i, wo, 16);
+  }
+  return 0;
+}
+
 // which: 0 = inv, 1 = invsqrt, 2 = dbl, 3 = half; 16-byte rows, input tight
 int sim_fp_op(int which, const uint8_t* a, uint8_t* out, size_t n) {
   for (size_t i = 0; i < n; i++) {

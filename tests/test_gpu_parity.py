@@ -21,7 +21,7 @@ def fq():
     return fourq_b200
 
 
-def R(lst):
+def R(lst, width=None):
     return np.frombuffer(b"".join(lst), np.uint8).reshape(len(lst), -1).copy()
 
 
@@ -43,6 +43,21 @@ def test_fp2_unary_golden(fq, golden, op):
     rows = golden["fields"][op]
     got = getattr(fq.GFp2, op)(R([H(r[0]) for r in rows]))
     assert hexrows(got) == [r[1] for r in rows]
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "sqr", "neg", "inv", "invsqrt"])
+def test_fp_rows_golden_and_random(fq, golden, op):
+    rows = golden["fp"][op]
+    binary = len(rows[0]) == 3
+    a = R([H(r[0]) for r in rows], 16)
+    got = getattr(fq.GFp, op)(a, R([H(r[1]) for r in rows], 16)) if binary else getattr(fq.GFp, op)(a)
+    assert hexrows(got) == [r[-1] for r in rows]
+    rng = np.random.default_rng(11)
+    n = 4096 if op in ("inv", "invsqrt") else 65536
+    x = rng.integers(0, 256, (n, 16), np.uint8); y = rng.integers(0, 256, (n, 16), np.uint8)
+    got = getattr(fq.GFp, op)(x, y) if binary else getattr(fq.GFp, op)(x)
+    idx = range(0, n, 16)
+    assert [bytes(got[j]) for j in idx] == [O.row_fp(op, bytes(x[j]), bytes(y[j]) if binary else None) for j in idx]
 
 
 def test_codec_golden(fq, golden):
@@ -219,6 +234,60 @@ def test_ragged_and_empty_batches(fq):
     assert (fq.MUL_base(k[-200:]) == full[-200:]).all()
     # non-contiguous input is accepted (copied)
     assert (fq.MUL_base(k[::2][:64]) == full[::2][:64]).all()
+
+
+def _oracle_dh_affine(args):
+    return O.row_dh_affine(args[0], args[1], mul=O.mul_endo if args[2] == "endo" else O.mul_windowed)
+
+
+def test_dh_ragged_batches_and_failures_next_to_good_rows(fq):
+    """Variable-base DH on batches that are not multiples of 128 or 4, with every failure class in the same inversion
+    groups as good rows (k_dh_finish shares one inversion between 4 rows): decode failures, the reference's t == 0 quirk,
+    neutral results (k = 0 mod N), against the oracle row by row; also the affine entry points and y_only."""
+    rng = np.random.default_rng(21)
+    n = 1003
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    pub = fq.MUL_base(rng.integers(0, 256, (n, 32), np.uint8))
+    pub[::5] = rng.integers(0, 256, (len(pub[::5]), 32), np.uint8)                      # arbitrary strings
+    quirk = np.frombuffer(O.encode((0, 0), (1, 0)), np.uint8)                          # (0, 1): status 3 in the reference
+    pub[3::50] = quirk
+    for j, m in zip(range(7, n, 40), [0, O.N, 2 * O.N, 5 * O.N, O.N - 1, O.N + 1, 1, 2] * 4):
+        k[j] = np.frombuffer(int(m).to_bytes(32, "little"), np.uint8)
+        pub[j] = np.frombuffer(O.encode(O.GX, O.GY), np.uint8)
+    with _pool() as pool:
+        want = pool.map(_oracle_dh, [(bytes(k[j]), bytes(pub[j])) for j in range(n)], chunksize=16)
+        assert {s for _, s in want} >= {0, 3, 4, 5}
+        for alg in ("endo", "windowed"):
+            for m in (n, 1, 3, 5, 127, 129, 515):
+                out, st = fq.DH(k[:m], pub[:m], algorithm=alg)
+                assert [(bytes(o), int(s)) for o, s in zip(out, st)] == want[:m], (alg, m)
+        ysec, st = fq.DH(k, pub, y_only=True)
+        assert [bytes(r) for r in ysec] == [bytes(o[:31] + bytes([o[31] & 0x7F])) for o, _ in want]
+        # affine entry points: valid points from decode, plus points off the curve (status 4)
+        XY, sd = fq.decode(pub)
+        XY[11::13, 5] ^= 1
+        want_aff = pool.map(_oracle_dh_affine, [(bytes(k[j]), bytes(XY[j]), "endo") for j in range(0, n, 3)], chunksize=16)
+        for fn in (fq.DH_endo, fq.DH_windowed):
+            out, st = fn(k, XY)
+            assert [(bytes(out[j]), int(st[j])) for j in range(0, n, 3)] == want_aff, fn.__name__
+
+
+def test_device_resident_batch_larger_than_one_launch_group(fq):
+    """fq_dev_run on more rows than one launch group of the DH kernels (2^22): the batches must tile the buffers exactly."""
+    from fourq_b200 import device as fqdev
+    n = (1 << 22) + 777
+    rng = np.random.default_rng(22)
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    pub = fq.MUL_base(rng.integers(0, 256, (n, 32), np.uint8))
+    dk = fqdev.DeviceBuffer.from_host(0, k); dp = fqdev.DeviceBuffer.from_host(0, pub)
+    do = fqdev.DeviceBuffer(0, n * 32); ds = fqdev.DeviceBuffer(0, n)
+    fqdev.dev_run("dh_endo", 0, dk, dp, do, ds, n)
+    got, st = do.to_host((n, 32)), ds.to_host((n,))
+    want, wst = fq.DH(k, pub)                                   # host path: chunks of 2^17 rows
+    assert not st.any() and not wst.any() and (got == want).all()
+    dko = fqdev.DeviceBuffer(0, n * 32)
+    fqdev.dev_run("mul_base_comb", 0, dk, None, dko, None, n)
+    assert (dko.to_host((n, 32)) == fq.MUL_base(k)).all()
 
 
 def test_pinned_host_buffers(fq):

@@ -55,6 +55,18 @@ def test_fp2_unary_golden(sim, golden, op):
     assert [g.hex() for g in got] == [r[1] for r in rows]
 
 
+FPOPS = {"mul": 0, "sqr": 1, "inv": 2, "add": 3, "sub": 4, "neg": 5, "invsqrt": 6}
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "sqr", "neg", "inv", "invsqrt"])
+def test_fp_rows_golden(sim, golden, op):
+    rows = golden["fp"][op]
+    a = _rows([H(r[0]) for r in rows]); out = np.zeros_like(a)
+    b = _rows([H(r[1]) for r in rows]) if len(rows[0]) == 3 else None
+    assert sim.sim_fp_row_op(FPOPS[op], _p(a), _p(b) if b is not None else None, _p(out), ctypes.c_size_t(len(rows))) == 0
+    assert [bytes(out[16 * i:16 * i + 16]).hex() for i in range(len(rows))] == [r[-1] for r in rows]
+
+
 def test_fp2_random_and_adversarial_vs_oracle(sim):
     rng = random.Random(7)
     p = O.P127

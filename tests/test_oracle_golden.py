@@ -34,6 +34,12 @@ def test_fp_inv_invsqrt(golden):
         assert O.fp_to_le(O.fp_invsqrt(int.from_bytes(H(x), "little"))).hex() == out
 
 
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "sqr", "neg", "inv", "invsqrt"])
+def test_fp_rows(golden, op):
+    for r in golden["fp"][op]:
+        assert O.row_fp(op, H(r[0]), H(r[1]) if len(r) == 3 else None).hex() == r[-1]
+
+
 def test_encode_decode(golden):
     c = golden["codec"]
     assert O.encode(O.GX, O.GY).hex() == c["Genc"] == "87b2cb2b46a224b95a7820a19bee3f0e5c8b4c8444c3a74942020e63f84a1c6e"
