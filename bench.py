@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--algorithm", default="endo", choices=["windowed", "endo"],
                     help="scalar-multiplication algorithm of the reference: MUL_windowed or MUL_endo (same outputs)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="rows of the CPU baseline sample (default 256 per core; 0 = skip)")
+    ap.add_argument("--verify-rows", type=int, default=-1, help="rows of rank 0's batch compared bit for bit with the C oracle after the timed regions (default all; 0 = skip)")
     args = ap.parse_args()
     out = _quiet_stdout()
 
@@ -332,6 +333,18 @@ def main():
                 raise SystemExit("PARITY FAILURE: GPU output differs from the oracle on the CPU-baseline sample")
             cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "first %d rows of rank 0's batch, oracle row_dh (DH_%s) under multiprocessing (%d procs); bit-exact with the GPU rows" % (sample, args.algorithm, cores)}
+        # every row of rank 0's batch against the C restatement of the reference (oracle/fourq_oracle.c), all host cores
+        parity = None
+        if args.verify_rows != 0:
+            from oracle import c_oracle
+            m = rows if args.verify_rows < 0 else min(rows, args.verify_rows)
+            t0 = time.perf_counter()
+            want, wst = c_oracle.dh(k[:m], pub[:m])
+            if not ((want == out_dev[:m]).all() and (wst == st_dev[:m]).all()):
+                raise SystemExit("PARITY FAILURE: GPU output differs from oracle/fourq_oracle.c")
+            parity = {"rows_checked": int(m), "bit_exact": True, "checker": "oracle/fourq_oracle.c (DH_windowed restatement, pinned to the reference's golden vectors)",
+                      "seconds": time.perf_counter() - t0}
+            parity["checker_rows_per_s"] = m / parity["seconds"]      # the C port on all host cores (threads), for scale
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",
@@ -342,7 +355,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * rows, "d2h_bytes_per_step": 33 * rows,
                         "note": "fourq_b200.DH(k, B, out=, status=) on pinned numpy arrays (inputs and outputs), wall clock, per GPU bytes"},
                 "gpu_launches": 3 * args.steps,
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
     barrier()
     if dist is not None:
         dist.destroy_process_group()

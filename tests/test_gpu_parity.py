@@ -222,6 +222,29 @@ def test_full_size_properties_2_20(fq):
     assert (fq.GFp2.mul(prod, fq.GFp2.inv(fb)) == fq.GFp2.mul(fa, fq.GFp2.mul(fb, fq.GFp2.inv(fb)))).all()
 
 
+def test_full_size_bit_exact_vs_c_oracle(fq):
+    """Every row of a BASELINE-size batch against oracle/fourq_oracle.c (pinned to the reference's golden vectors by
+    tests/test_oracle_c.py): 2^20 variable-base DH rows incl. undecodable strings, 2^20 fixed-base rows."""
+    from oracle import c_oracle as C
+    n = 1 << 20
+    rng = np.random.default_rng(41)
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    kp = rng.integers(0, 256, (n, 32), np.uint8)
+    pub = fq.MUL_base(kp)                                            # comb kernel
+    assert (pub == C.mul_base(kp)).all()
+    pub[::97] = rng.integers(0, 256, (len(pub[::97]), 32), np.uint8)   # ~1 % arbitrary strings: every decode failure class
+    want, wst = C.dh(k, pub)
+    got, st = fq.DH(k, pub)                                          # endo
+    assert (st == wst).all() and (got == want).all()
+    assert set(np.unique(wst)) >= {0, 4}
+    m = 1 << 18
+    got, st = fq.DH(k[:m], pub[:m], algorithm="windowed")
+    assert (st == wst[:m]).all() and (got == want[:m]).all()
+    gb, sb = fq.DH_base(k[:m])
+    wb, wsb = C.dh_base(k[:m])
+    assert (sb == wsb).all() and (gb == wb).all()
+
+
 def test_ragged_and_empty_batches(fq):
     rng = np.random.default_rng(6)
     assert fq.MUL_base(np.zeros((0, 32), np.uint8)).shape == (0, 32)
