@@ -216,6 +216,20 @@ def main():
         assert (st, Q) == (st2, Q2)
         mul["dh"].append([kbytes(k), enc.hex(), st, bytes(c4q.encode(*Q)).hex() if st == 0 else "00" * 32])
         mul["dh_affine"].append([kbytes(k), xyb(P), st, xyb(Q) if st == 0 else "00" * 64])
+    # BASELINE.json configs[0]: 1,024 random 32-byte scalars x the base point through the reference's DH_windowed with the
+    # table of [392]G (curve4q.py:743-762), encoded.  Scalars = numpy default_rng(1).integers(0, 256, (1024, 32), uint8)
+    # (SURVEY 8d cfg 1); stored as the SHA-256 of the scalars plus the 1,024 outputs.
+    import hashlib
+    import numpy as np
+    k1 = np.random.default_rng(1).integers(0, 256, (1024, 32), np.uint8)
+    outs = []
+    for row in k1:
+        st, Q = ref_dh_status(c4q.DH_windowed, int.from_bytes(bytes(row), "little"), G, T392w)
+        assert st == 0
+        outs.append(bytes(c4q.encode(*Q)).hex())
+    dump("cfg1.json", {"scalars": "numpy.random.default_rng(1).integers(0, 256, (1024, 32), numpy.uint8)",
+                       "scalars_sha256": hashlib.sha256(k1.tobytes()).hexdigest(), "out": outs})
+
     # failure paths of DH_core
     P392 = ((0x1318020702de23bc3c9b73c751b4b192, 0x77ab39a7d8990c0a18e3c409fbd81a95),
             (0x515854b6d19cc2da1ea2b43b5121a22e, 0x763f89e129497361d74dff5063e66682))     # curve4q.py:772-773

@@ -86,6 +86,20 @@ def test_scalar_mult_golden(fq, golden, alg):
     assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh_affine"]]
 
 
+def test_baseline_config1_reference_vectors(fq, golden):
+    """BASELINE.json configs[0]: 1,024 random scalars x the base point, outputs of the reference's own DH_windowed
+    (tests/golden/cfg1.json), through every fixed-base algorithm and through the variable-base kernels on encode(G)."""
+    k = np.random.default_rng(1).integers(0, 256, (1024, 32), np.uint8)
+    want = golden["cfg1"]["out"]
+    for alg in ("comb", "windowed", "endo"):
+        out, st = fq.DH_base(k, algorithm=alg)
+        assert not st.any() and hexrows(out) == want, alg
+    Genc = np.tile(np.frombuffer(O.encode(O.GX, O.GY), np.uint8), (1024, 1))
+    for alg in ("endo", "windowed"):
+        out, st = fq.DH(k, Genc, algorithm=alg)
+        assert not st.any() and hexrows(out) == want, alg
+
+
 def test_fixed_base_comb_golden(fq, golden):
     """Per-digit tables: same bytes as MUL_*(m, G, table) / DH_*(m, G, table=T392), incl. edge scalars."""
     m = golden["mul"]

@@ -241,3 +241,15 @@ def test_dh_endo_golden(sim, golden):
     sim.sim_dh_endo(_p(k), _p(e), _p(out), _p(st), ctypes.c_size_t(n))
     for i, (kk, ee, want_st, want) in enumerate(rows):
         assert (int(st[i]), bytes(out[32 * i:32 * i + 32]).hex()) == (want_st, want), (kk, ee)
+
+
+def test_baseline_config1_sample(sim, golden):
+    """BASELINE.json configs[0] on the instruction-level simulation of the device code (every 16th row, all three fixed-base
+    algorithms of the device: windowed table, endomorphism table, per-digit comb)."""
+    k = np.random.default_rng(1).integers(0, 256, (1024, 32), np.uint8)[::16].copy()
+    want = golden["cfg1"]["out"][::16]
+    n = len(k)
+    for fn, args in (("sim_fixed_base", (1,)), ("sim_fixed_base", (3,)), ("sim_comb", (1,))):       # bit 0 = dh, bit 1 = endo
+        out = np.zeros((n, 32), np.uint8); st = np.zeros(n, np.uint8)
+        assert getattr(sim, fn)(*args, _p(k), _p(out), _p(st), ctypes.c_size_t(n)) == 0
+        assert not st.any() and [bytes(r).hex() for r in out] == want, (fn, args)

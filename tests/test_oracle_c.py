@@ -74,3 +74,19 @@ def test_random_rows_vs_python_oracle():
     big_k = np.tile(k, (8, 1)); big_p = np.tile(pub, (8, 1))
     o2, s2 = C.dh(big_k, big_p, threads=8)
     assert (o2 == np.tile(out, (8, 1))).all() and (s2 == np.tile(st, 8)).all()
+
+
+def _cfg1_scalars(golden):
+    import hashlib
+    k = np.random.default_rng(1).integers(0, 256, (1024, 32), np.uint8)
+    assert hashlib.sha256(k.tobytes()).hexdigest() == golden["cfg1"]["scalars_sha256"]
+    return k
+
+
+def test_baseline_config1_reference_vectors(golden):
+    """BASELINE.json configs[0]: 1,024 scalars x G through the reference's DH_windowed (tests/golden/cfg1.json)."""
+    k = _cfg1_scalars(golden)
+    out, st = C.dh_base(k)
+    assert not st.any() and hexrows(out) == golden["cfg1"]["out"]
+    for j in range(0, 1024, 64):                                   # the Python oracle on a sample (6 ms per row)
+        assert O.row_dh_base(bytes(k[j])) == (H(golden["cfg1"]["out"][j]), 0)
