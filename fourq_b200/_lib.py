@@ -14,7 +14,7 @@ FQ_OK, FQ_ERR_NO_DEVICE, FQ_ERR_CUDA, FQ_ERR_ARG = 0, -1, -2, -3
 FPOP = {"mul": 0, "sqr": 1, "inv": 2, "add": 3, "sub": 4, "neg": 5, "invsqrt": 6}      # FQ_FP_* of the header
 DEVOP = {"fp_mul": 32, "fp_sqr": 33, "fp_inv": 34, "fp_add": 35, "fp_sub": 36, "fp_neg": 37, "fp_invsqrt": 38,
          "fp2_mul": 0, "fp2_sqr": 1, "fp2_inv": 2, "fp2_add": 3, "fp2_sub": 4, "fp2_neg": 5, "fp2_conj": 6,
-         "decode": 16, "encode": 17, "dh": 18, "dh_affine": 19, "dh_base": 20, "mul_base": 21, "x25519": 22,
+         "decode": 16, "decode_spec": 29, "encode": 17, "dh": 18, "dh_affine": 19, "dh_base": 20, "mul_base": 21, "x25519": 22,
          "dh_endo": 23, "dh_endo_affine": 24, "dh_endo_base": 25, "mul_endo_base": 26, "dh_base_comb": 27, "mul_base_comb": 28}
 
 
@@ -42,7 +42,7 @@ def lib():
         "fq_fp2_sqr": ([vp, vp, sz, i], i), "fq_fp2_inv": ([vp, vp, sz, i], i), "fq_fp2_neg": ([vp, vp, sz, i], i),
         "fq_fp2_conj": ([vp, vp, sz, i], i),
         "fq_fp_op": ([i, vp, vp, vp, sz, i], i),
-        "fq_decode": ([vp, vp, vp, sz, i], i), "fq_encode": ([vp, vp, sz, i], i),
+        "fq_decode": ([vp, vp, vp, sz, i], i), "fq_decode_spec": ([vp, vp, vp, sz, i], i), "fq_encode": ([vp, vp, sz, i], i),
         "fq_dh": ([vp, vp, vp, vp, sz, i], i), "fq_dh_affine": ([vp, vp, vp, vp, sz, i], i),
         "fq_dh_base": ([vp, vp, vp, sz, i], i), "fq_mul_base": ([vp, vp, sz, i], i),
         "fq_dh_endo": ([vp, vp, vp, vp, sz, i], i), "fq_dh_endo_affine": ([vp, vp, vp, vp, sz, i], i),
@@ -64,7 +64,7 @@ def lib():
 
 
 EXPORTS = ["fq_version", "fq_device_count", "fq_last_error", "fq_set_device_base", "fq_last_kernel_ms", "fq_fp2_mul",
-           "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_fp_op", "fq_decode", "fq_encode",
+           "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_fp_op", "fq_decode", "fq_decode_spec", "fq_encode",
            "fq_dh", "fq_dh_affine", "fq_dh_base", "fq_mul_base", "fq_dh_endo", "fq_dh_endo_affine", "fq_dh_endo_base",
            "fq_mul_endo_base", "fq_dh_base_comb", "fq_mul_base_comb", "fq_x25519", "fq_host_alloc", "fq_host_free",
            "fq_dev_alloc", "fq_dev_free", "fq_dev_upload", "fq_dev_download", "fq_dev_run", "fq_dev_last_phase_ms", "fq_dev_flush_l2", "fq_imad_peak"]

@@ -120,7 +120,7 @@ OpDesc describe(int op) {
     case FQ_DEVOP_FP_BASE + FQ_FP_MUL: case FQ_DEVOP_FP_BASE + FQ_FP_ADD: case FQ_DEVOP_FP_BASE + FQ_FP_SUB: return {op, 16, 16, 16, false, (size_t)1 << 20};
     case FQ_DEVOP_FP_BASE + FQ_FP_SQR: case FQ_DEVOP_FP_BASE + FQ_FP_NEG: return {op, 16, 0, 16, false, (size_t)1 << 20};
     case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT: return {op, 16, 0, 16, false, (size_t)1 << 18};
-    case FQ_DEVOP_DECODE: return {op, 32, 0, 64, true, (size_t)1 << 18};
+    case FQ_DEVOP_DECODE: case FQ_DEVOP_DECODE_SPEC: return {op, 32, 0, 64, true, (size_t)1 << 18};
     case FQ_DEVOP_ENCODE: return {op, 64, 0, 32, false, (size_t)1 << 20};
     case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, 32, 32, 32, true, dh_chunk_rows()};
     case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, dh_chunk_rows()};
@@ -148,7 +148,8 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_FP_BASE + FQ_FP_MUL: case FQ_DEVOP_FP_BASE + FQ_FP_SQR: case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_ADD:
     case FQ_DEVOP_FP_BASE + FQ_FP_SUB: case FQ_DEVOP_FP_BASE + FQ_FP_NEG: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT:
       return fqk_fp_op(op - FQ_DEVOP_FP_BASE, a, b, out, n, s);
-    case FQ_DEVOP_DECODE: return fqk_decode(a, out, status, n, s);
+    case FQ_DEVOP_DECODE: return fqk_decode(0, a, out, status, n, s);
+    case FQ_DEVOP_DECODE_SPEC: return fqk_decode(1, a, out, status, n, s);
     case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
     case FQ_DEVOP_DH: return fqk_dh(0, 0, a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, a, b, out, status, n, cx.dh_scratch[si], s, ev);
@@ -276,6 +277,7 @@ int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n,
   return run_host(FQ_DEVOP_FP_BASE + op, a, b, out, nullptr, n, ndev);
 }
 int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE, enc, nullptr, xy, status, n, ndev); }
+int fq_decode_spec(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE_SPEC, enc, nullptr, xy, status, n, ndev); }
 int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev) { return run_host(FQ_DEVOP_ENCODE, xy, nullptr, enc, nullptr, n, ndev); }
 int fq_dh(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH, k, enc_pt, enc_out, status, n, ndev); }
 int fq_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_AFFINE, k, xy, xy_out, status, n, ndev); }

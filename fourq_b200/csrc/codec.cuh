@@ -25,7 +25,10 @@ FQ_FN void pt_encode(const fp2& x, const fp2& y, u32* out) {
 }
 
 // curve4q.py:49-96.  in = 8 little-endian words of the 32-byte string.  Returns the status; x, y canonical when OK.
-FQ_FN u32 pt_decode(const u32* in, fp2& x, fp2& y) {
+// SPEC = false (default everywhere): bit-compatible with the reference, which raises AttributeError when t == 0
+// (curve4q.py:76-77 calls a GFp.two that does not exist) -> FQ_ST_QUIRK_T0.  SPEC = true (fq_decode_spec only): what the
+// draft specifies there, t = 2 (t0 - t3) (draft-ladd-cfrg-4q.md:865-867), so the encodings of (0, +-1) and (+-i, 0) decode.
+template <bool SPEC = false> FQ_FN u32 pt_decode(const u32* in, fp2& x, fp2& y) {
   u32 st = FQ_ST_OK;
   if (in[3] >> 31) st = FQ_ST_RESERVED_BIT;                                   // :52  B[15] & 0x80
   u32 s = in[7] >> 31;                                                        // :55
@@ -45,7 +48,8 @@ FQ_FN u32 pt_decode(const u32* in, fp2& x, fp2& y) {
   fp t3 = fp_add(fp_sqr(t0), fp_sqr(t1));                                     // :72
   t3 = fp_mul(fp_invsqrt_c(t3), t3);                                            // :73
   fp t = fp_dbl(fp_add(t0, t3));                                              // :75
-  if (st == FQ_ST_OK && fp_is_zero(t)) st = FQ_ST_QUIRK_T0;                   // :76-77 (the reference raises here)
+  if (SPEC) { if (fp_is_zero(t)) t = fp_dbl(fp_sub(t0, t3)); }                // draft :865-867
+  else if (st == FQ_ST_OK && fp_is_zero(t)) st = FQ_ST_QUIRK_T0;              // :76-77 (the reference raises here)
   fpb T2 = fp_prep(t2);
   fp a = fp_invsqrt_c(fp_mul(fp_mul_prep(fp_sqr(t2), T2), t));                  // :79
   fp at2 = fp_mul_prep(a, T2);

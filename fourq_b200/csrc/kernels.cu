@@ -26,12 +26,12 @@ template <int OP> __global__ void __launch_bounds__(256) k_fp_op(const uint4* __
   out[row] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
 }
 
-__global__ void __launch_bounds__(256) k_decode(const void* enc, void* xy, unsigned char* status, size_t n) {
+template <bool SPEC> __global__ void __launch_bounds__(256) k_decode(const void* enc, void* xy, unsigned char* status, size_t n) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   u32 we[8], wo[16];
   ld8(enc, row, we);
-  status[row] = (unsigned char)row_decode(we, wo);
+  status[row] = (unsigned char)row_decode<SPEC>(we, wo);
   st8(xy, 2 * row, wo); st8(xy, 2 * row + 1, wo + 8);
 }
 
@@ -136,9 +136,10 @@ cudaError_t fqk_fp_op(int op, const void* a, const void* b, void* out, size_t n,
   }
   return cudaGetLastError();
 }
-cudaError_t fqk_decode(const void* enc, void* xy, void* status, size_t n, cudaStream_t s) {
+cudaError_t fqk_decode(int spec, const void* enc, void* xy, void* status, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  k_decode<<<grid_for(n, 256), 256, 0, s>>>(enc, xy, (unsigned char*)status, n);
+  if (spec) k_decode<true><<<grid_for(n, 256), 256, 0, s>>>(enc, xy, (unsigned char*)status, n);
+  else k_decode<false><<<grid_for(n, 256), 256, 0, s>>>(enc, xy, (unsigned char*)status, n);
   return cudaGetLastError();
 }
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s) {

@@ -8,7 +8,7 @@ enum { FQK_MUL = 0, FQK_SQR = 1, FQK_INV = 2, FQK_ADD = 3, FQK_SUB = 4, FQK_NEG 
 cudaError_t fqk_device_init(cudaStream_t s);   // once per device: fixed-base tables -> __constant__, smem opt-in
 cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_fp_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);   // GF(p), 16-byte rows, op = FQ_FP_* of the header
-cudaError_t fqk_decode(const void* enc, void* xy, void* status, size_t n, cudaStream_t s);
+cudaError_t fqk_decode(int spec, const void* enc, void* xy, void* status, size_t n, cudaStream_t s);   // spec: draft's t == 0 branch instead of the reference's exception
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s);
 // variable-base DH = three kernels (prepare, ladder, finish; kernels_dh.cuh) that hand the per-row table and the projective
 // result over through `scratch`, a device buffer of at least fqk_dh_scratch_bytes(n) bytes owned by the caller.

@@ -53,9 +53,9 @@ template <int OP> FQ_FN void row_fp_op(const u32* a, const u32* b, u32* out) {
 }
 
 // decode: 8 words -> 16 words (x0|x1|y0|y1), zero-filled on failure
-FQ_FN u32 row_decode(const u32* enc, u32* xy) {
+template <bool SPEC = false> FQ_FN u32 row_decode(const u32* enc, u32* xy) {
   fp2 x, y;
-  u32 st = pt_decode(enc, x, y);
+  u32 st = pt_decode<SPEC>(enc, x, y);
   if (st != FQ_ST_OK) { x = fp2_zero(); y = fp2_zero(); }
   row_store_fp2(xy, x); row_store_fp2(xy + 8, y);
   return st;

@@ -81,12 +81,16 @@ def encode(XY, ndev=1, out=None):
     return out
 
 
-def decode(B, ndev=1, strict=False, out=None, status=None):
+def decode(B, ndev=1, strict=False, out=None, status=None, spec=False):
+    """decode (curve4q.py:49-96).  spec=True is an opt-in that is NOT bit-compatible with the reference on four inputs: it
+    decodes as the draft specifies (t = 2 (t0 - t3) when t == 0, draft-ladd-cfrg-4q.md:865-867) where the reference raises
+    AttributeError (status 3), so the encodings of (0, 1), (0, -1), (i, 0), (-i, 0) decode; everything else is unchanged."""
     B = _lib.rows(B, 32, "B")
     n = B.shape[0]
     XY = _buf(out, (n, 64), "out")
     status = _buf(status, (n,), "status")
-    _lib.check(_lib.lib().fq_decode(_lib.ptr(B), _lib.ptr(XY), _lib.ptr(status), n, ndev))
+    fn = _lib.lib().fq_decode_spec if spec else _lib.lib().fq_decode
+    _lib.check(fn(_lib.ptr(B), _lib.ptr(XY), _lib.ptr(status), n, ndev))
     if strict:
         _raise_first(status)
     return XY, status

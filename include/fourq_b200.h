@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 103
+#define FQ_VERSION 104
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -82,6 +82,11 @@ FQ_API int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, si
  * Unlike the reference, decode does not modify its input. */
 FQ_API int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev);
 FQ_API int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev);
+/* Opt-in, NOT bit-compatible with the reference on four inputs: decode as the draft specifies it (draft-ladd-cfrg-4q.md:841-888).
+ * The reference raises AttributeError when t == 0 (curve4q.py:76-77, status 3 above); the draft continues with
+ * t = 2 (t0 - t3), which decodes the encodings of the low-order points (0, 1), (0, -1), (i, 0), (-i, 0).  Every other input
+ * gives exactly what fq_decode gives; status 3 never occurs. */
+FQ_API int fq_decode_spec(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev);
 
 /* ---- Diffie-Hellman
  * fq_dh:        encode(DH_windowed(k, decode(enc_pt)))            curve4q.py:49, 446-465, 41
@@ -128,6 +133,7 @@ FQ_API int fq_host_free(void* p);
 #define FQ_DEVOP_FP_BASE 32    /* FQ_DEVOP_FP_BASE + FQ_FP_*: GF(p) ops on 16-byte rows, a (, b), out */
 #define FQ_DEVOP_DECODE 16     /* a = enc, out = xy, status */
 #define FQ_DEVOP_ENCODE 17     /* a = xy, out = enc */
+#define FQ_DEVOP_DECODE_SPEC 29   /* as FQ_DEVOP_DECODE with the draft's t == 0 branch (fq_decode_spec) */
 #define FQ_DEVOP_DH 18         /* a = k, b = enc_pt, out, status */
 #define FQ_DEVOP_DH_AFFINE 19  /* a = k, b = xy, out = xy, status */
 #define FQ_DEVOP_DH_BASE 20    /* a = k, out, status */

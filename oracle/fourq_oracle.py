@@ -167,8 +167,9 @@ def encode(x, y):            # curve4q.py:41-46
     return bytes(out)
 
 
-def decode_status(B):
-    """curve4q.py:49-96 -> (status, (x, y) or None).  Length must be 32 (checked by the caller)."""
+def decode_status(B, spec=False):
+    """curve4q.py:49-96 -> (status, (x, y) or None).  Length must be 32 (checked by the caller).
+    spec=True follows the draft where the reference crashes: t = 2 (t0 - t3) when t == 0 (draft-ladd-cfrg-4q.md:865-867)."""
     B = bytes(B)
     if len(B) != 32:
         raise ValueError("Malformed point: length {} != 32".format(len(B)))   # curve4q.py:50-51
@@ -190,7 +191,9 @@ def decode_status(B):
     t3 = fp_mul(fp_invsqrt(t3), t3)                                           # :73  sqrt(|u conj v|^2)
     t = fp_mul(2, fp_add(t0, t3))                                             # :75
     if t == 0:                                                                # :76-77 reference crashes here
-        return ST_QUIRK_T0, None
+        if not spec:
+            return ST_QUIRK_T0, None
+        t = fp_mul(2, fp_sub(t0, t3))                                         # what :77 means (draft :865-867)
     a = fp_invsqrt(fp_mul(t, fp_mul(t2, fp_sqr(t2))))                         # :79
     b = fp_mul(fp_mul(a, t2), t)                                              # :80
     x0 = fp_mul(b, 1 << 126)                                                  # :82  (GFp.half)
@@ -559,8 +562,8 @@ def row_mul_base(k):
     return encode(Q[0], Q[1])
 
 
-def row_decode(enc):
-    st, P = decode_status(enc)
+def row_decode(enc, spec=False):
+    st, P = decode_status(enc, spec)
     if st != ST_OK:
         return bytes(64), st
     return xy_to_bytes(P), ST_OK

@@ -81,6 +81,14 @@ int sim_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n) {
   }
   return 0;
 }
+int sim_decode_spec(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 we[8], wo[16]; memcpy(we, enc + 32 * i, 32);
+    status[i] = (uint8_t)row_decode<true>(we, wo);
+    memcpy(xy + 64 * i, wo, 64);
+  }
+  return 0;
+}
 int sim_encode(const uint8_t* xy, uint8_t* enc, size_t n) {
   for (size_t i = 0; i < n; i++) {
     u32 wi[16], wo[8]; memcpy(wi, xy + 64 * i, 64);

@@ -86,6 +86,20 @@ def test_scalar_mult_golden(fq, golden, alg):
     assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh_affine"]]
 
 
+def test_decode_spec_opt_in(fq, golden):
+    rows = golden["codec"]["decode"]
+    low = [O.encode(x, y) for x, y in (((0, 0), (1, 0)), ((0, 0), (O.P127 - 1, 0)), ((0, 1), (0, 0)), ((0, O.P127 - 1), (0, 0)))]
+    enc = R([H(r[0]) for r in rows] + low)
+    xy, st = fq.decode(enc, spec=True)
+    want = [O.row_decode(bytes(e), spec=True) for e in enc]
+    assert [(bytes(a), int(b)) for a, b in zip(xy, st)] == want
+    assert not st[-4:].any() and 3 not in set(int(s) for s in st)
+    xy0, st0 = fq.decode(enc)                                      # default stays bit-compatible: the four are status 3
+    assert list(st0[-4:]) == [3, 3, 3, 3]
+    keep = st0 != 3
+    assert (xy[keep] == xy0[keep]).all() and (st[keep] == st0[keep]).all()
+
+
 def test_baseline_config1_reference_vectors(fq, golden):
     """BASELINE.json configs[0]: 1,024 random scalars x the base point, outputs of the reference's own DH_windowed
     (tests/golden/cfg1.json), through every fixed-base algorithm and through the variable-base kernels on encode(G)."""

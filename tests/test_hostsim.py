@@ -253,3 +253,15 @@ def test_baseline_config1_sample(sim, golden):
         out = np.zeros((n, 32), np.uint8); st = np.zeros(n, np.uint8)
         assert getattr(sim, fn)(*args, _p(k), _p(out), _p(st), ctypes.c_size_t(n)) == 0
         assert not st.any() and [bytes(r).hex() for r in out] == want, (fn, args)
+
+
+def test_decode_spec_opt_in(sim, golden):
+    rows = [r for r in golden["codec"]["decode"]]
+    low = [O.encode(x, y) for x, y in (((0, 0), (1, 0)), ((0, 0), (O.P127 - 1, 0)), ((0, 1), (0, 0)), ((0, O.P127 - 1), (0, 0)))]
+    enc = _rows([H(r[0]) for r in rows] + low)
+    n = len(rows) + len(low)
+    xy = np.zeros(64 * n, np.uint8); st = np.zeros(n, np.uint8)
+    assert sim.sim_decode_spec(_p(enc), _p(xy), _p(st), ctypes.c_size_t(n)) == 0
+    want = [O.row_decode(bytes(enc[32 * i:32 * i + 32]), spec=True) for i in range(n)]
+    assert [(bytes(xy[64 * i:64 * i + 64]), int(st[i])) for i in range(n)] == want
+    assert not st[-4:].any() and 3 not in set(int(s) for s in st)

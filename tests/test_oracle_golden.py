@@ -53,6 +53,23 @@ def test_encode_decode(golden):
     assert seen == {0, 1, 2, 3, 4}
 
 
+LOW_ORDER = [((0, 0), (1, 0)), ((0, 0), (O.P127 - 1, 0)), ((0, 1), (0, 0)), ((0, O.P127 - 1), (0, 0))]     # (0,1) (0,-1) (i,0) (-i,0)
+
+
+def test_decode_spec_opt_in(golden):
+    """spec=True: the draft's t == 0 branch (draft-ladd-cfrg-4q.md:865-867) decodes the four low-order encodings the reference
+    crashes on; every other input of the reference-generated decode vectors is unchanged."""
+    for x, y in LOW_ORDER:
+        enc = O.encode(x, y)
+        assert O.row_decode(enc)[1] == O.ST_QUIRK_T0
+        xy, st = O.row_decode(enc, spec=True)
+        assert st == 0 and xy == O.xy_to_bytes((x, y)) and O.on_curve((x, y))
+    for enc, st, xy in golden["codec"]["decode"]:
+        if st != O.ST_QUIRK_T0:
+            got_xy, got_st = O.row_decode(H(enc), spec=True)
+            assert (got_st, got_xy.hex()) == (st, xy), enc
+
+
 def test_decode_does_not_mutate():
     b = bytearray(H("87b2cb2b46a224b95a7820a19bee3f0e5c8b4c8444c3a74942020e63f84a1cee"))
     keep = bytes(b)
