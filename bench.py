@@ -349,7 +349,7 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "algorithm": "MUL_%s (curve4q.py:%s)" % (args.algorithm, "405-442" if args.algorithm == "endo" else "188-235"),
-                           "rows_per_gpu": rows, "l2": "flushed (256 MiB memset) between timed iterations",
+                           "table_select": "strict scan" if fq.get_select_mode() else "masked loads", "rows_per_gpu": rows, "l2": "flushed (256 MiB memset) between timed iterations",
                            "timing": "CUDA events around the three kernels of each step (k_dh_prep, k_dh_ladder, k_dh_finish), summed over steps, max over ranks", "wall_s_timed_region": wall},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * rows, "d2h_bytes_per_step": 33 * rows,

@@ -26,6 +26,7 @@ thread_local float tl_kernel_ms = 0.f;
 thread_local float tl_phase_ms[3] = {0.f, 0.f, 0.f};
 std::mutex g_mu;
 int g_dev_base = 0;
+int g_strict = -1;            // table selection: 0 = masked loads (default), 1 = strict scan, -1 = not yet read from FQ_STRICT_SELECT
 
 int fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(tl_err, sizeof(tl_err), fmt, ap); va_end(ap);
@@ -79,6 +80,11 @@ int slot_reserve(Slot& s, int which, size_t bytes) {
 bool is_dh_op(int op) { return op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE || op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE; }
 bool is_comb_op(int op) { return op == FQ_DEVOP_DH_BASE_COMB || op == FQ_DEVOP_MUL_BASE_COMB; }
 bool needs_scratch(int op) { return is_dh_op(op) || is_comb_op(op); }
+
+int strict_mode() {
+  if (g_strict < 0) { const char* e = getenv("FQ_STRICT_SELECT"); g_strict = (e && e[0] == '1') ? 1 : 0; }
+  return g_strict;
+}
 
 // grows the kernel scratch of stream slot `si` to what `op` needs for `rows` rows
 int dh_scratch_reserve(DevCtx& c, int si, int op, size_t rows) {
@@ -136,8 +142,8 @@ OpDesc describe(int op) {
 // si: stream slot whose DH scratch is used (reserved by the caller); ev: optional per-kernel events of the DH pipeline
 cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s, int si = 0, cudaEvent_t* ev = nullptr) {
   switch (op) {
-    case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, cx.comb, a, out, status, n, cx.dh_scratch[si], cx.sms, s);
-    case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, cx.comb, a, out, nullptr, n, cx.dh_scratch[si], cx.sms, s);
+    case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, strict_mode(), cx.comb, a, out, status, n, cx.dh_scratch[si], cx.sms, s);
+    case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, strict_mode(), cx.comb, a, out, nullptr, n, cx.dh_scratch[si], cx.sms, s);
     case FQ_DEVOP_FP2_MUL: return fqk_fp2_op(FQK_MUL, a, b, out, n, s);
     case FQ_DEVOP_FP2_SQR: return fqk_fp2_op(FQK_SQR, a, b, out, n, s);
     case FQ_DEVOP_FP2_INV: return fqk_fp2_op(FQK_INV, a, b, out, n, s);
@@ -151,14 +157,14 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_DECODE: return fqk_decode(0, a, out, status, n, s);
     case FQ_DEVOP_DECODE_SPEC: return fqk_decode(1, a, out, status, n, s);
     case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
-    case FQ_DEVOP_DH: return fqk_dh(0, 0, a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, a, out, status, n, s);
-    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, a, out, nullptr, n, s);
-    case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, a, out, status, n, s);
-    case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, a, out, nullptr, n, s);
+    case FQ_DEVOP_DH: return fqk_dh(0, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
+    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
+    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, strict_mode(), a, out, status, n, s);
+    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, strict_mode(), a, out, nullptr, n, s);
+    case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
+    case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
+    case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, strict_mode(), a, out, status, n, s);
+    case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, strict_mode(), a, out, nullptr, n, s);
     case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, s);
     default: return cudaErrorInvalidValue;
   }
@@ -263,6 +269,17 @@ int fq_set_device_base(int first) {
   if (first < 0 || first >= count) return fail(FQ_ERR_ARG, "device base %d out of range (%d device(s))", first, count);
   g_dev_base = first;
   return FQ_OK;
+}
+
+int fq_set_select_mode(int strict) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (strict != 0 && strict != 1) return fail(FQ_ERR_ARG, "select mode must be 0 (masked loads) or 1 (strict scan)");
+  g_strict = strict;
+  return FQ_OK;
+}
+int fq_get_select_mode(void) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  return strict_mode();
 }
 
 int fq_fp2_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_MUL, a, b, out, nullptr, n, ndev); }

@@ -45,7 +45,7 @@ FQ_FN ptA3 a3_load(const u32* w) {
 // constant-time T_i[idx] with the sign applied (curve4q.py:193-195: -(N, D, F) = (D, N, -F)); tab = the 192 words of T_i in
 // shared memory (16-byte aligned).  Entry 7 is loaded unconditionally, entries 0..6 under the digit's predicate (dh.cuh
 // quad_take): 6 LDS.128 per entry, the same addresses in every thread (broadcast).
-FQ_FN ptA3 comb_select(const u32* tab, u32 idx, u32 neg) {
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptA3 comb_select(const u32* tab, u32 idx, u32 neg) {
   const uint4* t4 = reinterpret_cast<const uint4*>(tab);
   fp w[6];
   FQ_UNROLL
@@ -54,7 +54,7 @@ FQ_FN ptA3 comb_select(const u32* tab, u32 idx, u32 neg) {
   for (int e = 0; e < 7; e++) {
     const bool c = idx == (u32)e;
     FQ_UNROLL
-    for (int q = 0; q < 6; q++) quad_take(t4 + e * 6 + q, w[q], c);
+    for (int q = 0; q < 6; q++) quad_take<STRICT>(t4 + e * 6 + q, w[q], c);
   }
   ptA3 P, R;
   P.N = fp2_set(w[0], w[1]); P.D = fp2_set(w[2], w[3]); P.F = fp2_set(w[4], w[5]);
@@ -65,7 +65,7 @@ FQ_FN ptA3 comb_select(const u32* tab, u32 idx, u32 neg) {
 }
 
 // [k]B for the base point whose tables are `tab` (FQ_COMB_WORDS words); returns R1
-FQ_FN ptR1 mul_comb(const scal& k, const u32* tab) {
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 mul_comb(const scal& k, const u32* tab) {
   MulPlan pl = plan_windowed(k);
   // leading digit d_62 = +1: start from T_62[0] = [16^62]B, back in (x, y) from (x+y, y-x)
   ptA3 S = a3_load(tab + 62 * FQ_COMB_DIGIT_WORDS);
@@ -76,7 +76,7 @@ FQ_FN ptR1 mul_comb(const scal& k, const u32* tab) {
   for (int i = 61; i >= 0; i--) {
     u32 idx, neg;
     scal_next_digit(pl.S, idx, neg);
-    Q = pt_madd(Q, comb_select(tab + i * FQ_COMB_DIGIT_WORDS, idx, neg));
+    Q = pt_madd(Q, comb_select<STRICT>(tab + i * FQ_COMB_DIGIT_WORDS, idx, neg));
   }
   return Q;
 }

@@ -32,36 +32,53 @@ FQ_FN ptR2 tab_load(const TabView& T, int e) {
 }
 
 // Constant-time table selection.  Every thread issues the loads of ALL entries in the same order from addresses that do not
-// depend on the digit; the digit only sets the predicate ("mask") of each load.
-//   default           masked loads: `@p ld.shared.v4` -- a lane whose predicate is off transfers nothing and keeps its
-//                     registers, so the select costs no ALU instruction at all (56 LDS.128 per select).
-//   FQ_STRICT_SELECT  every lane loads every entry and each word goes through one SEL per entry (56 LDS.128 + 224 SEL).
+// depend on the digit; the digit only decides what each load keeps.  Two variants, compiled side by side and chosen per
+// launch (template parameter STRICT; fq_set_select_mode / FQ_STRICT_SELECT=1 at run time):
+//   masked loads (library default)  `@p ld.shared.v4` -- a lane whose predicate is off transfers nothing and keeps its
+//                            registers, so the select costs no ALU instruction at all (56 LDS.128 per select).  The number of
+//                            shared-memory wavefronts of a load then depends on which lanes are on: a batch in which all 32
+//                            rows of every warp pick the same entry runs the ladder 0.4 % faster than one in which they differ
+//                            (tools/ct_timing.py, profiles/r01_ct_timing.jsonl).
+//   strict scan              every lane loads every entry and each word goes through one SEL per entry (56 LDS.128 + 224
+//                            SEL): no data-dependent memory activity of any kind, no measurable timing difference; the
+//                            ladder is 1-3 % slower, the fixed-base comb kernel (short iterations) 8 %.
 // No secret-dependent branch or address in either; the layout [entry][quad][thread] keeps lane L on banks 4L..4L+3 for
-// every entry, so there is no digit-dependent bank conflict.
+// every entry, so there is no digit-dependent bank conflict.  (The template default below only concerns code that does not
+// pass STRICT explicitly: the CPU simulation and the experiments in tools/kexp.)
+#ifdef FQ_STRICT_SELECT
+#define FQ_STRICT_DEFAULT true
+#else
+#define FQ_STRICT_DEFAULT false
+#endif
+
 // w = c ? *p : w for one 16-byte quad; p points into shared memory
-FQ_FN void quad_take(const uint4* p, fp& w, bool c) {
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN void quad_take(const uint4* p, fp& w, bool c) {
 #if defined(FQ_HOSTSIM)
   if (c) w = fp_set(p->x, p->y, p->z, p->w);
-#elif defined(FQ_STRICT_SELECT)
-  u32 a0, a1, a2, a3;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"((u32)__cvta_generic_to_shared(p)));
-  w.v[0] = c ? a0 : w.v[0]; w.v[1] = c ? a1 : w.v[1]; w.v[2] = c ? a2 : w.v[2]; w.v[3] = c ? a3 : w.v[3];
 #else
-  asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4]; }"
-               : "+r"(w.v[0]), "+r"(w.v[1]), "+r"(w.v[2]), "+r"(w.v[3]) : "r"((u32)__cvta_generic_to_shared(p)), "r"((u32)c));
+  if (STRICT) {
+    u32 a0, a1, a2, a3;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"((u32)__cvta_generic_to_shared(p)));
+    w.v[0] = c ? a0 : w.v[0]; w.v[1] = c ? a1 : w.v[1]; w.v[2] = c ? a2 : w.v[2]; w.v[3] = c ? a3 : w.v[3];
+  } else {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4]; }"
+                 : "+r"(w.v[0]), "+r"(w.v[1]), "+r"(w.v[2]), "+r"(w.v[3]) : "r"((u32)__cvta_generic_to_shared(p)), "r"((u32)c));
+  }
 #endif
 }
-FQ_FN void tab_take(const TabView& T, int e, int q, fp& w, bool c) { quad_take(T.base + (e * 8 + q) * T.stride, w, c); }
-FQ_FN void tab_take_r2(const TabView& T, int e, ptR2& w, bool c) {
-  tab_take(T, e, 0, w.N.re, c); tab_take(T, e, 1, w.N.im, c); tab_take(T, e, 2, w.D.re, c); tab_take(T, e, 3, w.D.im, c);
-  tab_take(T, e, 4, w.E.re, c); tab_take(T, e, 5, w.E.im, c); tab_take(T, e, 6, w.F.re, c); tab_take(T, e, 7, w.F.im, c);
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN void tab_take(const TabView& T, int e, int q, fp& w, bool c) {
+  quad_take<STRICT>(T.base + (e * 8 + q) * T.stride, w, c);
+}
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN void tab_take_r2(const TabView& T, int e, ptR2& w, bool c) {
+  tab_take<STRICT>(T, e, 0, w.N.re, c); tab_take<STRICT>(T, e, 1, w.N.im, c); tab_take<STRICT>(T, e, 2, w.D.re, c); tab_take<STRICT>(T, e, 3, w.D.im, c);
+  tab_take<STRICT>(T, e, 4, w.E.re, c); tab_take<STRICT>(T, e, 5, w.E.im, c); tab_take<STRICT>(T, e, 6, w.F.re, c); tab_take<STRICT>(T, e, 7, w.F.im, c);
 }
 
 // T[idx]: starts from the register-resident entry 7 and scans entries 0..6 in shared memory
-FQ_FN ptR2 tab_select(const TabView& T, const ptR2& T7, u32 idx) {
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR2 tab_select(const TabView& T, const ptR2& T7, u32 idx) {
   ptR2 S = T7;
   FQ_UNROLL
-  for (int e = 0; e < 7; e++) tab_take_r2(T, e, S, idx == (u32)e);
+  for (int e = 0; e < 7; e++) tab_take_r2<STRICT>(T, e, S, idx == (u32)e);
   return S;
 }
 
@@ -108,9 +125,9 @@ template <class SELECT> FQ_FN ptR1 mul_windowed(const scal& k, SELECT select) {
   return loop_windowed(pl, select);
 }
 
-struct SelectShared {
+template <bool STRICT = FQ_STRICT_DEFAULT> struct SelectShared {
   TabView T; ptR2 T7;
-  FQ_MFN ptR2 operator()(u32 idx) const { return tab_select(T, T7, idx); }
+  FQ_MFN ptR2 operator()(u32 idx) const { return tab_select<STRICT>(T, T7, idx); }
 };
 
 // DH_core (curve4q.py:446-462) after the point has been validated, in three phases so that a kernel can keep all warps
@@ -128,20 +145,20 @@ FQ_FN void dh_setup_windowed(const scal& k, const fp2& x, const fp2& y, const Ta
   D.T7 = tab_build(T, Q);
   D.plan = plan_windowed(k);
 }
-FQ_FN ptR1 dh_loop_windowed(const TabView& T, DhState& D) {
-  SelectShared sel; sel.T = T; sel.T7 = D.T7;
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 dh_loop_windowed(const TabView& T, DhState& D) {
+  SelectShared<STRICT> sel; sel.T = T; sel.T7 = D.T7;
   return loop_windowed(D.plan, sel);
 }
 
 // fixed base (the reference's table_windowed / table_endo shape): ONE table of 8 entries x 8 quads shared by all threads
 // of a CTA, held in shared memory as [entry][quad] (stride 1).  Every thread reads the same address (broadcast), entry 7 is
 // loaded unconditionally and entries 0..6 under the digit's predicate, exactly like tab_select.
-struct SelectBroadcast {
+template <bool STRICT = FQ_STRICT_DEFAULT> struct SelectBroadcast {
   TabView T;
   FQ_MFN ptR2 operator()(u32 idx) const {
     ptR2 S = tab_load(T, 7);
     FQ_UNROLL
-    for (int e = 0; e < 7; e++) tab_take_r2(T, e, S, idx == (u32)e);
+    for (int e = 0; e < 7; e++) tab_take_r2<STRICT>(T, e, S, idx == (u32)e);
     return S;
   }
 };
@@ -152,8 +169,8 @@ FQ_FN void r2_to_words(const ptR2& P, u32* w) {
 }
 
 // [k]B for the base point whose table is T; returns canonical affine.  MUL_windowed(k, ., table) + R1toAffine.
-FQ_FN void mul_fixed_base(const scal& k, const TabView& T, fp2& ox, fp2& oy) {
-  SelectBroadcast sel; sel.T = T;
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN void mul_fixed_base(const scal& k, const TabView& T, fp2& ox, fp2& oy) {
+  SelectBroadcast<STRICT> sel; sel.T = T;
   ptR1 R = mul_windowed(k, sel);
   pt_to_affine(R, ox, oy);
 }

@@ -216,7 +216,7 @@ FQ_FN void dh_setup_endo(const scal& k, const fp2& x, const fp2& y, const TabVie
   D.T7 = endo_tab_build(T, Q);
   D.plan = plan_endo(k);
 }
-FQ_FN ptR1 dh_loop_endo(const TabView& T, DhState& D) {
-  SelectShared sel; sel.T = T; sel.T7 = D.T7;
+template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 dh_loop_endo(const TabView& T, DhState& D) {
+  SelectShared<STRICT> sel; sel.T = T; sel.T7 = D.T7;
   return loop_endo(D.plan, sel);
 }

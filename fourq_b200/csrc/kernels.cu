@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_
 
 // fixed base: [k]G (DH = false) or [k][392]G with neutral rejection (DH = true).  The CTA copies the 1 KiB table of its base
 // point from the constant bank into shared memory once; the selection then reads it by broadcast (dh.cuh SelectBroadcast).
-template <bool DH, bool ENDO> __global__ void __launch_bounds__(256)
+template <bool DH, bool ENDO, bool STRICT> __global__ void __launch_bounds__(256)
 k_fixed_base(const void* k, void* out, unsigned char* status, size_t n) {
   __shared__ uint4 stab[64];
   if (threadIdx.x < 64) {
@@ -58,7 +58,7 @@ k_fixed_base(const void* k, void* out, unsigned char* status, size_t n) {
   if (row >= n) return;
   u32 wk[8], wo[8];
   ld8(k, row, wk);
-  u32 st = row_fixed_base<DH, ENDO>(wk, stab, wo);
+  u32 st = row_fixed_base<DH, ENDO, STRICT>(wk, stab, wo);
   if (status) status[row] = (unsigned char)st;
   st8(out, row, wo);
 }
@@ -154,18 +154,21 @@ size_t fqk_dh_scratch_bytes(size_t n) {
   size_t npad = (rows + 127) / 128 * 128;
   return npad * (72 * 16 + 4);
 }
-cudaError_t fqk_dh(int affine, int endo, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev) {
+cudaError_t fqk_dh(int affine, int endo, int strict, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev) {
   if (n == 0) return cudaSuccess;
-  return endo ? fqk_dh_endo(affine, k, pt, out, status, n, scratch, s, ev) : fqk_dh_windowed(affine, k, pt, out, status, n, scratch, s, ev);
+  return endo ? fqk_dh_endo(affine, strict, k, pt, out, status, n, scratch, s, ev) : fqk_dh_windowed(affine, strict, k, pt, out, status, n, scratch, s, ev);
 }
-cudaError_t fqk_fixed_base(int dh, int endo, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
+template <bool STRICT> static void fixed_base_launch(int dh, int endo, unsigned g, const void* k, void* out, unsigned char* st, size_t n, cudaStream_t s) {
+  if (dh && endo) k_fixed_base<true, true, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
+  else if (dh) k_fixed_base<true, false, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
+  else if (endo) k_fixed_base<false, true, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
+  else k_fixed_base<false, false, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
+}
+cudaError_t fqk_fixed_base(int dh, int endo, int strict, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   unsigned g = grid_for(n, 256);
-  unsigned char* st = (unsigned char*)status;
-  if (dh && endo) k_fixed_base<true, true><<<g, 256, 0, s>>>(k, out, st, n);
-  else if (dh) k_fixed_base<true, false><<<g, 256, 0, s>>>(k, out, st, n);
-  else if (endo) k_fixed_base<false, true><<<g, 256, 0, s>>>(k, out, st, n);
-  else k_fixed_base<false, false><<<g, 256, 0, s>>>(k, out, st, n);
+  if (strict) fixed_base_launch<true>(dh, endo, g, k, out, (unsigned char*)status, n, s);
+  else fixed_base_launch<false>(dh, endo, g, k, out, (unsigned char*)status, n, s);
   return cudaGetLastError();
 }
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s) {

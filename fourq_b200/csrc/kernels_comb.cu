@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(64) k_comb_build(u32* tabs) {
 }
 
 // [k]B in R1 for every row; (X, Y, Z) go to scratch for k_dh_finish (one inversion per FQ_FIN_ROWS rows, encode)
-template <bool DH> __global__ void __launch_bounds__(FQ_COMB_THREADS)
+template <bool DH, bool STRICT> __global__ void __launch_bounds__(FQ_COMB_THREADS)
 k_comb(const u32* __restrict__ tabs, const void* __restrict__ k, DhScratch sc, size_t n) {
   extern __shared__ uint4 stab4[];
   const uint4* src = reinterpret_cast<const uint4*>(tabs + (DH ? FQ_COMB_WORDS : 0));
@@ -32,7 +32,7 @@ k_comb(const u32* __restrict__ tabs, const void* __restrict__ k, DhScratch sc, s
     scal sk;
     FQ_UNROLL
     for (int i = 0; i < 8; i++) sk.v[i] = wk[i];
-    ptR1 R = mul_comb(sk, stab);
+    ptR1 R = mul_comb<STRICT>(sk, stab);
     uint4* o = sc.R + row;
     stq(o, R.X.re); stq(o + sc.npad, R.X.im); stq(o + 2 * sc.npad, R.Y.re); stq(o + 3 * sc.npad, R.Y.im);
     stq(o + 4 * sc.npad, R.Z.re); stq(o + 5 * sc.npad, R.Z.im);
@@ -44,8 +44,10 @@ cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s) {
   cudaError_t e;
   u32* tabs = nullptr;
   if ((e = cudaMalloc(&tabs, 2 * FQ_COMB_WORDS * sizeof(u32))) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_comb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_comb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_comb<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_comb<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_comb<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_comb<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
   k_comb_build<<<(2 * FQ_COMB_DIGITS + 63) / 64, 64, 0, s>>>(tabs);
   if ((e = cudaGetLastError()) != cudaSuccess) { cudaFree(tabs); return e; }
   if ((e = cudaStreamSynchronize(s)) != cudaSuccess) { cudaFree(tabs); return e; }
@@ -55,7 +57,7 @@ cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s) {
 
 size_t fqk_comb_scratch_bytes(size_t n) { return fin_scratch_bytes(n < FQ_DH_MAX_BATCH ? n : FQ_DH_MAX_BATCH); }
 
-cudaError_t fqk_comb(int dh, const void* tabs, const void* k, void* out, void* status, size_t n, void* scratch, int sms, cudaStream_t s) {
+cudaError_t fqk_comb(int dh, int strict, const void* tabs, const void* k, void* out, void* status, size_t n, void* scratch, int sms, cudaStream_t s) {
   for (size_t r0 = 0; r0 < n; r0 += FQ_DH_MAX_BATCH) {
     const size_t rows = n - r0 < FQ_DH_MAX_BATCH ? n - r0 : FQ_DH_MAX_BATCH;
     DhScratch sc = fin_scratch_view(scratch, rows);
@@ -66,10 +68,12 @@ cudaError_t fqk_comb(int dh, const void* tabs, const void* k, void* out, void* s
     const char* kk = (const char*)k + 32 * r0; char* oo = (char*)out + 32 * r0;
     unsigned char* st = status ? (unsigned char*)status + r0 : nullptr;
     if (dh) {
-      k_comb<true><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
+      if (strict) k_comb<true, true><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
+      else k_comb<true, false><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
       k_dh_finish<false, true><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
     } else {
-      k_comb<false><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
+      if (strict) k_comb<false, true><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
+      else k_comb<false, false><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
       k_dh_finish<false, false><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
     }
     cudaError_t e = cudaGetLastError();

@@ -88,7 +88,7 @@ k_dh_prep(const void* __restrict__ k, const void* __restrict__ pt, DhScratch sc,
   sc.meta[row] = D.plan.first | (st << 8);
 }
 
-template <bool ENDO> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
+template <bool ENDO, bool STRICT> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
 k_dh_ladder(DhScratch sc) {
   extern __shared__ uint4 smem[];
   const size_t row = (size_t)blockIdx.x * FQ_DH_THREADS + threadIdx.x;
@@ -102,7 +102,7 @@ k_dh_ladder(DhScratch sc) {
   D.plan.S.v[0] = s0.x; D.plan.S.v[1] = s0.y; D.plan.S.v[2] = s0.z; D.plan.S.v[3] = s0.w;
   D.plan.S.v[4] = s1.x; D.plan.S.v[5] = s1.y; D.plan.S.v[6] = s1.z; D.plan.S.v[7] = s1.w;
   D.plan.first = sc.meta[row] & 0xffu;
-  ptR1 R = row_dh_loop<ENDO>(T, D);
+  ptR1 R = row_dh_loop<ENDO, STRICT>(T, D);
   uint4* o = sc.R + row;
   stq(o, R.X.re); stq(o + sc.npad, R.X.im); stq(o + 2 * sc.npad, R.Y.re); stq(o + 3 * sc.npad, R.Y.im);
   stq(o + 4 * sc.npad, R.Z.re); stq(o + 5 * sc.npad, R.Z.im);
@@ -171,11 +171,14 @@ static inline DhScratch fin_scratch_view(void* base, size_t rows) {
 }
 
 template <bool ENDO> static cudaError_t dh_init() {
-  return cudaFuncSetAttribute(k_dh_ladder<ENDO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(k_dh_ladder<ENDO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_dh_ladder<ENDO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_DH_SMEM);
 }
 // scratch: dh_scratch_bytes(min(n, FQ_DH_MAX_BATCH)) bytes on the device.  ev: optional 4 events recorded around the three
 // kernels of the (last) batch, for per-kernel timing.
-template <bool ENDO> static cudaError_t dh_launch(int affine, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch,
+// strict: table selection by the strict scan instead of masked loads (dh.cuh)
+template <bool ENDO> static cudaError_t dh_launch(int affine, int strict, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch,
                                                   cudaStream_t s, cudaEvent_t* ev) {
   const size_t in_pt = affine ? 64 : 32, out_b = affine ? 64 : 32;
   for (size_t r0 = 0; r0 < n; r0 += FQ_DH_MAX_BATCH) {
@@ -189,7 +192,8 @@ template <bool ENDO> static cudaError_t dh_launch(int affine, const void* k, con
     if (affine) k_dh_prep<true, ENDO><<<g, FQ_DH_THREADS, 0, s>>>(kk, pp, sc, rows);
     else k_dh_prep<false, ENDO><<<g, FQ_DH_THREADS, 0, s>>>(kk, pp, sc, rows);
     if (ev) cudaEventRecord(ev[1], s);
-    k_dh_ladder<ENDO><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(sc);
+    if (strict) k_dh_ladder<ENDO, true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(sc);
+    else k_dh_ladder<ENDO, false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(sc);
     if (ev) cudaEventRecord(ev[2], s);
     if (affine) k_dh_finish<true, true><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
     else k_dh_finish<false, true><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);

@@ -84,7 +84,7 @@ template <bool ENDO, bool AFFINE> FQ_FN u32 row_dh_setup(const u32* k, const u32
   if (ENDO) dh_setup_endo(row_load_scalar(k), x, y, T, D); else dh_setup_windowed(row_load_scalar(k), x, y, T, D);
   return st;
 }
-template <bool ENDO> FQ_FN ptR1 row_dh_loop(const TabView& T, DhState& D) { return ENDO ? dh_loop_endo(T, D) : dh_loop_windowed(T, D); }
+template <bool ENDO, bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 row_dh_loop(const TabView& T, DhState& D) { return ENDO ? dh_loop_endo<STRICT>(T, D) : dh_loop_windowed<STRICT>(T, D); }
 template <bool AFFINE> FQ_FN u32 row_dh_finish(u32 st, const ptR1& R, u32* out) {
   fp2 ox, oy;
   u32 st2 = dh_finish(R, ox, oy);
@@ -105,11 +105,11 @@ template <bool ENDO> FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* o
 }
 // fq_mul_base (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base (true): encode([k][392]G) with the neutral check
 // tab: the 64 quads of the base point's table, [entry][quad], in shared memory on the device
-template <bool CHECK_NEUTRAL, bool ENDO> FQ_FN u32 row_fixed_base(const u32* k, uint4* tab, u32* out) {
+template <bool CHECK_NEUTRAL, bool ENDO, bool STRICT = FQ_STRICT_DEFAULT> FQ_FN u32 row_fixed_base(const u32* k, uint4* tab, u32* out) {
   fp2 ox, oy;
   TabView T; T.base = tab; T.stride = 1;
-  if (ENDO) { SelectBroadcast sel; sel.T = T; pt_to_affine(mul_endo(row_load_scalar(k), sel), ox, oy); }
-  else mul_fixed_base(row_load_scalar(k), T, ox, oy);
+  if (ENDO) { SelectBroadcast<STRICT> sel; sel.T = T; pt_to_affine(mul_endo(row_load_scalar(k), sel), ox, oy); }
+  else mul_fixed_base<STRICT>(row_load_scalar(k), T, ox, oy);
   u32 st = FQ_ST_OK;
   if (CHECK_NEUTRAL && (fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one()))) st = FQ_ST_NEUTRAL;
   if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);

@@ -18,6 +18,18 @@ def set_device(first):
     _lib.check(_lib.lib().fq_set_device_base(int(first)))
 
 
+def set_select_mode(strict):
+    """Table selection of every scalar multiplication: False = masked loads (default: predicated loads, no select
+    instructions; the shared-memory activity of a load depends on how the digits are spread over a warp), True = strict scan
+    (every lane loads every entry and selects in registers; DH 1-2 % slower, comb keygen 8 % slower).  Same outputs.
+    FQ_STRICT_SELECT=1 selects the strict scan at start-up."""
+    _lib.check(_lib.lib().fq_set_select_mode(1 if strict else 0))
+
+
+def get_select_mode():
+    return bool(_lib.lib().fq_get_select_mode())
+
+
 def last_kernel_ms():
     return float(_lib.lib().fq_last_kernel_ms())
 

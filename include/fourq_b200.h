@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 104
+#define FQ_VERSION 105
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -55,6 +55,19 @@ FQ_API const char* fq_last_error(void);
 FQ_API int fq_set_device_base(int first);
 /* kernel-only milliseconds (CUDA events, max over devices of the per-device sum) of the last host call of this thread */
 FQ_API float fq_last_kernel_ms(void);
+
+/* Constant-time table selection of every scalar multiplication (csrc/dh.cuh).  In both modes every thread issues the loads
+ * of ALL table entries from digit-independent addresses and there is no secret-dependent branch.
+ *   0 (default)  masked loads: the digit sets each load's predicate and a lane whose predicate is off transfers nothing; no
+ *                select instructions at all.  The number of shared-memory wavefronts of a load then depends on how the
+ *                digits are distributed over the 32 lanes of a warp: 0.4 % of the ladder time between the extremes "all rows
+ *                of every warp use the same scalar" and "all differ" (profiles/r01_ct_timing.jsonl).
+ *   1            strict scan: every lane loads every entry and keeps one with a predicated select per word, so not even the
+ *                memory activity of a load depends on a digit (no measurable timing difference); variable-base DH 1-2 %
+ *                slower, fixed-base comb keygen 8 % slower.
+ * Same outputs.  The environment variable FQ_STRICT_SELECT=1 selects 1 at start-up. */
+FQ_API int fq_set_select_mode(int strict);
+FQ_API int fq_get_select_mode(void);
 
 /* ---- GF(p^2) field ops: fields.py GFp2.mul :167, sqr :176, inv :194, add :157, sub :162, neg :184, conj :189.
  * Inputs may be any 128-bit values per half (the reference reduces ints mod p); outputs are canonical. */

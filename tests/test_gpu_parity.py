@@ -86,6 +86,36 @@ def test_scalar_mult_golden(fq, golden, alg):
     assert [(int(s), o) for s, o in zip(st, hexrows(out))] == [(r[2], r[3]) for r in m["dh_affine"]]
 
 
+def test_strict_select_mode_gives_identical_outputs(fq):
+    """fq_set_select_mode: the masked loads (default, predicated LDS) and the strict scan (every lane loads every table
+    entry, SEL per word); every scalar-multiplication kernel must give the same bytes in both modes."""
+    rng = np.random.default_rng(61)
+    n = 20000
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    pub = fq.MUL_base(rng.integers(0, 256, (n, 32), np.uint8))
+    pub[::11] = rng.integers(0, 256, (len(pub[::11]), 32), np.uint8)
+    default = fq.get_select_mode()
+    ref = {}
+    try:
+        for strict in (True, False):
+            fq.set_select_mode(strict)
+            assert fq.get_select_mode() is strict
+            got = {"dh_endo": fq.DH(k, pub, algorithm="endo"), "dh_win": fq.DH(k, pub, algorithm="windowed")}
+            for alg in ("comb", "endo", "windowed"):
+                got["mul_" + alg] = (fq.MUL_base(k, algorithm=alg),)
+                got["dhb_" + alg] = fq.DH_base(k, algorithm=alg)
+            if strict:
+                ref = got
+            else:
+                for name in ref:
+                    assert all((a == b).all() for a, b in zip(ref[name], got[name])), name
+    finally:
+        fq.set_select_mode(default)
+    from oracle import c_oracle as C
+    want, wst = C.dh(k, pub)
+    assert (ref["dh_endo"][0] == want).all() and (ref["dh_endo"][1] == wst).all()
+
+
 def test_decode_spec_opt_in(fq, golden):
     rows = golden["codec"]["decode"]
     low = [O.encode(x, y) for x, y in (((0, 0), (1, 0)), ((0, 0), (O.P127 - 1, 0)), ((0, 1), (0, 0)), ((0, O.P127 - 1), (0, 0)))]

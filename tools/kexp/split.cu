@@ -10,8 +10,6 @@
 
 struct Scratch { uint4* tab; uint4* plan; u32* meta; uint4* R; size_t npad; };
 
-__device__ __forceinline__ void stq(uint4* p, const fp& a) { *p = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); }
-__device__ __forceinline__ fp ldq(const uint4* p) { uint4 w = *p; return fp_set(w.x, w.y, w.z, w.w); }
 
 template <bool ENDO, int MINB> __global__ void __launch_bounds__(128, MINB)
 k_prep(const void* __restrict__ k, const void* __restrict__ pt, Scratch sc, size_t n) {
