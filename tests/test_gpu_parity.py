@@ -303,6 +303,40 @@ def test_full_size_bit_exact_vs_c_oracle(fq):
     assert (sb == wsb).all() and (gb == wb).all()
 
 
+def test_adversarial_grid_vs_c_oracle(fq):
+    """tests/adversarial.py: limb patterns built to break carry chains, folds, recoding and decoding -- GF(p^2) and GF(p) ops on
+    boundary and non-canonical values, and ~1,000 DH rows of special scalars x valid / invalid points, in both algorithms and
+    both table-selection modes, against the C oracle."""
+    import adversarial as A
+    from oracle import c_oracle as C
+    a, b = A.fp2_grid()
+    for op in ("mul", "add", "sub"):
+        assert (getattr(fq.GFp2, op)(a, b) == C.fp2(op, a, b)).all(), op
+        assert (getattr(fq.GFp, op)(a[:, :16], b[:, :16]) == C.fp(op, a[:, :16], b[:, :16])).all(), op
+    for op in ("sqr", "inv", "neg", "conj"):
+        ar = a.copy() if op in ("sqr", "inv") else C.fp2("add", a, np.zeros_like(a))      # neg / conj: reduced input as in the reference
+        assert (getattr(fq.GFp2, op)(ar) == C.fp2(op, ar)).all(), op
+    for op in ("sqr", "inv", "invsqrt"):
+        assert (getattr(fq.GFp, op)(a[:, :16]) == C.fp(op, a[:, :16])).all(), op
+    k, enc = A.grid()
+    want, wst = C.dh(k, enc)
+    assert set(int(x) for x in wst) >= {0, 3, 4, 5}
+    default = fq.get_select_mode()
+    try:
+        for strict in (False, True):
+            fq.set_select_mode(strict)
+            for alg in ("endo", "windowed"):
+                out, st = fq.DH(k, enc, algorithm=alg)
+                assert (st == wst).all() and (out == want).all(), (strict, alg)
+    finally:
+        fq.set_select_mode(default)
+    ks = k[:: 7]
+    for alg in ("comb", "endo", "windowed"):
+        assert (fq.MUL_base(ks, algorithm=alg) == C.mul_base(ks)).all(), alg
+        gb, sb = fq.DH_base(ks, algorithm=alg); wb, wsb = C.dh_base(ks)
+        assert (gb == wb).all() and (sb == wsb).all(), alg
+
+
 def test_ragged_and_empty_batches(fq):
     rng = np.random.default_rng(6)
     assert fq.MUL_base(np.zeros((0, 32), np.uint8)).shape == (0, 32)

@@ -265,3 +265,25 @@ def test_decode_spec_opt_in(sim, golden):
     want = [O.row_decode(bytes(enc[32 * i:32 * i + 32]), spec=True) for i in range(n)]
     assert [(bytes(xy[64 * i:64 * i + 64]), int(st[i])) for i in range(n)] == want
     assert not st[-4:].any() and 3 not in set(int(s) for s in st)
+
+
+def test_adversarial_grid_vs_c_oracle(sim):
+    """Carry chains, Mersenne folds, recoding and decoding of the DEVICE code (instruction-level simulation) on limb patterns
+    built to break them (tests/adversarial.py), against the C oracle: GF(p^2) ops on all-ones / boundary limbs and
+    non-canonical inputs, and whole Diffie-Hellman rows (both algorithms) on special scalars x valid and invalid points."""
+    import adversarial as A
+    from oracle import c_oracle as C
+    a, b = A.fp2_grid()
+    n = len(a)
+    for op in ("mul", "add", "sub", "sqr", "inv"):
+        out = np.zeros_like(a)
+        assert sim.sim_fp2_op(OPS[op], _p(a), _p(b) if op in ("mul", "add", "sub") else None, _p(out), ctypes.c_size_t(n)) == 0
+        assert (out == C.fp2(op, a, b if op in ("mul", "add", "sub") else None)).all(), op
+    k, enc = A.grid()
+    n = len(k)
+    want, wst = C.dh(k, enc)
+    assert set(int(x) for x in wst) >= {0, 4, 5}
+    for fn in ("sim_dh", "sim_dh_endo"):
+        out = np.zeros((n, 32), np.uint8); st = np.zeros(n, np.uint8)
+        assert getattr(sim, fn)(_p(k), _p(enc), _p(out), _p(st), ctypes.c_size_t(n)) == 0
+        assert (st == wst).all() and (out == want).all(), fn
