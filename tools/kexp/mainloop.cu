@@ -30,7 +30,11 @@ template <int MINB, int NSLOT> __global__ void __launch_bounds__(128, MINB) k_ma
   for (int e = 0; e < NSLOT; e++) for (int q = 0; q < 8; q++) tab_put(T, e, q, fp_set(wk[q], wk[(q + e) & 7], wk[(q + 3) & 7], wk[e & 7] & 0x7fffffffu));
   SelectSlots<NSLOT> sel; sel.T = T;
   ptR1 Q = pt_r2_to_r4(sel(wk[0] & 7));
+#ifdef FQ_EXP_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
   for (int i = 63; i >= 0; i--) {
     pt_dbl(Q);
     u32 idx, neg;
