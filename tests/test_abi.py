@@ -67,3 +67,21 @@ def test_product_never_imports_the_oracle():
                 # comments may mention the test oracle; code must not import, include, load or call it
                 assert not re.search(r"(import|from|include|CDLL|dlopen)[^\n]*oracle", src), f
                 assert not re.search(r"(import|from|CDLL|dlopen)[^\n]*hostsim", src), f
+
+
+def test_c_example_compiles_links_and_fails_loudly_without_a_gpu(libpath, tmp_path):
+    """examples/dh_example.c binds the C ABI from plain C; without a CUDA device it must exit with the no-device error."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "dh_example")
+    libdir = os.path.dirname(libpath)
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "examples", "dh_example.c"), "-L", libdir, "-lfourq_b200", "-Wl,-rpath," + libdir])
+    from fourq_b200 import _lib
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if _lib.lib().fq_device_count() > 0:
+        assert r.returncode == 0 and "shared secrets agree" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU path" in r.stderr
