@@ -405,6 +405,29 @@ def test_device_resident_batch_larger_than_one_launch_group(fq):
     assert (dko.to_host((n, 32)) == fq.MUL_base(k)).all()
 
 
+def test_argument_errors_are_reported_not_swallowed(fq):
+    rng = np.random.default_rng(71)
+    k = rng.integers(0, 256, (8, 32), np.uint8)
+    with pytest.raises(fq.FourQError, match="ndev"):
+        fq.MUL_base(k, ndev=fq.device_count() + 1)
+    with pytest.raises(ValueError):
+        fq.DH(k, k[:4])
+    with pytest.raises(ValueError):
+        fq.DH(k, np.zeros((8, 31), np.uint8))
+    with pytest.raises(TypeError):
+        fq.MUL_base(k.astype(np.int32))
+    with pytest.raises(ValueError):
+        fq.MUL_base(k, algorithm="nope")
+    with pytest.raises(ValueError):
+        fq.MUL_base(k, out=np.zeros((7, 32), np.uint8))
+    from fourq_b200 import _lib
+    assert _lib.lib().fq_fp_op(99, _lib.ptr(k), None, _lib.ptr(k), 1, 1) == _lib.FQ_ERR_ARG
+    assert _lib.lib().fq_set_select_mode(7) == _lib.FQ_ERR_ARG
+    assert b"select mode" in _lib.lib().fq_last_error()
+    assert _lib.lib().fq_dh(None, None, None, None, 5, 1) == _lib.FQ_ERR_ARG          # null buffers with n > 0
+    assert _lib.lib().fq_dh(None, None, None, None, 0, 1) == _lib.FQ_OK               # n = 0 touches nothing
+
+
 def test_pinned_host_buffers(fq):
     rng = np.random.default_rng(8)
     k = fq.pinned_empty((5000, 32)); k[:] = rng.integers(0, 256, (5000, 32), np.uint8)
