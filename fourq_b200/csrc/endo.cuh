@@ -87,14 +87,16 @@ FQ_FN ptR1 endo_psi(const ptR1& P) { return endo_tau_dual(endo_chi(endo_tau(pt3_
 // ---------------------------------------------------------------- decomposition (curve4q.py:326-356)
 // t_i = floor(L_i m / 2^256) is needed mod 2^64 only (the four results are < 2^64): limbs 8 and 9 of the 7 x 8 limb
 // product, by column sums with a 3-word carry-save accumulator.
-template <int W> FQ_FN u64 endo_mulhi_256(const u32 (&L)[W], const u32* m) {
+// One out-of-line body shared by the four constants (the fully inlined version was 4 x 170 straight-line instructions).
+FQ_CALL u64 endo_mulhi_256(u32 l0, u32 l1, u32 l2, u32 l3, u32 l4, u32 l5, u32 l6, scal m) {
+  const u32 L[7] = {l0, l1, l2, l3, l4, l5, l6};
   u32 c0 = 0, c1 = 0, c2 = 0, out8 = 0, out9 = 0;
   FQ_UNROLL
   for (int k = 0; k < 10; k++) {
     FQ_UNROLL
-    for (int i = 0; i < W; i++) {
+    for (int i = 0; i < 7; i++) {
       const int j = k - i;
-      if (j >= 0 && j < 8) { c0 = mad_lo_cc(L[i], m[j], c0); c1 = madc_hi_cc(L[i], m[j], c1); c2 = addc(c2, 0); }
+      if (j >= 0 && j < 8) { c0 = mad_lo_cc(L[i], m.v[j], c0); c1 = madc_hi_cc(L[i], m.v[j], c1); c2 = addc(c2, 0); }
     }
     if (k == 8) out8 = c0;
     if (k == 9) out9 = c0;
@@ -106,10 +108,7 @@ template <int W> FQ_FN u64 endo_mulhi_256(const u32 (&L)[W], const u32* m) {
 struct scal4 { u64 v[4]; };
 
 FQ_FN scal4 endo_decompose(const scal& m) {
-  const u32 L1[7] = {0x9d1a7d4fu, 0x259686e0u, 0xe6a6bd66u, 0xf75682acu, 0xea2be5dfu, 0xfc5bb5c5u, 0x00000007u};
-  const u32 L2[7] = {0xdd627afbu, 0xd1ba1d84u, 0x0f468d8du, 0x2bd23558u, 0xaa6c0f8au, 0x8fd4b04cu, 0x00000003u};
-  const u32 L3[6] = {0x678c203cu, 0x9b291a33u, 0x65dca902u, 0xc42bd6c9u, 0x0bffbaf6u, 0xd038bf8du};
-  const u32 L4[7] = {0x77e7fdc0u, 0x12e5666bu, 0x14983d82u, 0x81cbdc37u, 0xa22d8410u, 0x1b073877u, 0x00000003u};
+  // L1..L4 (curve4q.py:333-336), little-endian 32-bit limbs (L3 has 6: its 7th is 0)
   // lattice basis and offsets mod 2^64 (curve4q.py:326-337; negative entries wrapped)
   const u64 B1[4] = {0x0906ff27e0a0a196ull, 0xec9c179d3dd5d260ull, 0x07426031ecc8030full, 0xf7b08c66794619afull};
   const u64 B2[4] = {0x1d495bea84fcc2d4ull, 0xffffffffffffffffull, 0x0000000000000001ull, 0x25dbc5bc8dd167d0ull};
@@ -117,7 +116,10 @@ FQ_FN scal4 endo_decompose(const scal& m) {
   const u64 B4[4] = {0x136e340a9108c83full, 0x3122df2dc3e0ff32ull, 0xf975b60fd557564bull, 0xe72af7876921f516ull};
   const u64 C[4] = {0x72482c5251a4559cull, 0x59f95b0add276f6cull, 0x7dd2d17c4625fa78ull, 0x6bc57def56ce8877ull};
   const u64 CP[4] = {0x85b6605ce2ad1ddbull, 0x8b1c3a38a1086e9eull, 0x7748878c1b7d50c3ull, 0x52f07576bff07d8dull};
-  u64 t1 = endo_mulhi_256(L1, m.v), t2 = endo_mulhi_256(L2, m.v), t3 = endo_mulhi_256(L3, m.v), t4 = endo_mulhi_256(L4, m.v);
+  u64 t1 = endo_mulhi_256(0x9d1a7d4fu, 0x259686e0u, 0xe6a6bd66u, 0xf75682acu, 0xea2be5dfu, 0xfc5bb5c5u, 0x00000007u, m);
+  u64 t2 = endo_mulhi_256(0xdd627afbu, 0xd1ba1d84u, 0x0f468d8du, 0x2bd23558u, 0xaa6c0f8au, 0x8fd4b04cu, 0x00000003u, m);
+  u64 t3 = endo_mulhi_256(0x678c203cu, 0x9b291a33u, 0x65dca902u, 0xc42bd6c9u, 0x0bffbaf6u, 0xd038bf8du, 0x00000000u, m);
+  u64 t4 = endo_mulhi_256(0x77e7fdc0u, 0x12e5666bu, 0x14983d82u, 0x81cbdc37u, 0xa22d8410u, 0x1b073877u, 0x00000003u, m);
   scal4 a;
   FQ_UNROLL
   for (int j = 0; j < 4; j++) {
@@ -134,20 +136,24 @@ FQ_FN scal4 endo_decompose(const scal& m) {
 // ---------------------------------------------------------------- GLV-SAC recoding (curve4q.py:358-380)
 // Digit i (0..63) is packed as nibble i of S: bit 3 = sign (1 = positive), bits 0..2 = table index.  Returns d[64].
 FQ_FN u32 endo_recode(const scal4& vin, scal& S) {
-  u64 v0 = vin.v[0], v1 = vin.v[1], v2 = vin.v[2], v3 = vin.v[3];
+  u64 v0s = vin.v[0] >> 1, v1 = vin.v[1], v2 = vin.v[2], v3 = vin.v[3];     // v0s: bit i+1 of v0 is its bit 0 in step i (0 for i = 63)
   FQ_UNROLL
-  for (int w = 0; w < 8; w++) {
+  for (int w = 0; w < 8; w++) S.v[w] = 0;
+  FQ_NOUNROLL
+  for (int w = 0; w < 8; w++) {                  // rolled: the unrolled 64 steps were 2,000 straight-line instructions
     u32 word = 0;
     FQ_UNROLL
     for (int n = 0; n < 8; n++) {
-      const int i = 8 * w + n;
-      u32 b1 = (i + 1 < 64) ? (u32)((v0 >> (i + 1)) & 1ull) : 0u;
+      u32 b1 = (u32)(v0s & 1ull);
+      v0s >>= 1;
       u32 e1 = (u32)(v1 & 1ull), e2 = (u32)(v2 & 1ull), e3 = (u32)(v3 & 1ull);
       word |= ((b1 << 3) | e1 | (e2 << 1) | (e3 << 2)) << (4 * n);
       u32 nb1 = b1 ^ 1u;
       v1 = (v1 >> 1) + (u64)(nb1 & e1); v2 = (v2 >> 1) + (u64)(nb1 & e2); v3 = (v3 >> 1) + (u64)(nb1 & e3);
     }
-    S.v[w] = word;
+    FQ_UNROLL
+    for (int i = 0; i < 7; i++) S.v[i] = S.v[i + 1];          // word w ends up in S.v[w] after the 8 rounds
+    S.v[7] = word;
   }
   return (u32)(v1 + 2ull * v2 + 4ull * v3);
 }
