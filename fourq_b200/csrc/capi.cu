@@ -132,8 +132,9 @@ OpDesc describe(int op) {
     case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, dh_chunk_rows()};
     case FQ_DEVOP_DH_BASE: case FQ_DEVOP_DH_ENDO_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
     case FQ_DEVOP_MUL_BASE: case FQ_DEVOP_MUL_ENDO_BASE: return {op, 32, 0, 32, false, (size_t)1 << 17};
-    case FQ_DEVOP_DH_BASE_COMB: return {op, 32, 0, 32, true, (size_t)1 << 18};
-    case FQ_DEVOP_MUL_BASE_COMB: return {op, 32, 0, 32, false, (size_t)1 << 18};
+    // k_comb keeps 2 CTAs of 256 rows resident per SM, each walking over tiles: 148 x 2 x 256 x 4 rows = 4 full tiles per CTA
+    case FQ_DEVOP_DH_BASE_COMB: return {op, 32, 0, 32, true, (size_t)148 * 2 * 256 * 4};
+    case FQ_DEVOP_MUL_BASE_COMB: return {op, 32, 0, 32, false, (size_t)148 * 2 * 256 * 4};
     case FQ_DEVOP_X25519: return {op, 32, 32, 32, false, (size_t)1 << 17};
     default: return {-1, 0, 0, 0, false, 0};
   }

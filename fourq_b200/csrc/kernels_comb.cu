@@ -63,7 +63,9 @@ cudaError_t fqk_comb(int dh, int strict, const void* tabs, const void* k, void* 
     DhScratch sc = fin_scratch_view(scratch, rows);
     // persistent CTAs: the table copy (47 KiB) is paid once per CTA, each CTA then walks over tiles of 256 rows
     unsigned tiles = grid_for(rows, FQ_COMB_THREADS);
-    unsigned cap = (unsigned)sms * 4u;
+    // two CTAs are resident per SM (128 registers x 256 threads).  Big launches run two waves of CTAs (better balance at the
+    // end); chunk-sized launches run one, so that the 47 KiB table copy of a CTA is shared by 4 tiles instead of 2
+    unsigned cap = (unsigned)sms * (tiles >= (unsigned)sms * 16u ? 4u : 2u);
     unsigned g = tiles < cap ? tiles : cap;
     const char* kk = (const char*)k + 32 * r0; char* oo = (char*)out + 32 * r0;
     unsigned char* st = status ? (unsigned char*)status + r0 : nullptr;
