@@ -99,14 +99,14 @@ int dh_scratch_reserve(DevCtx& c, int si, int op, size_t rows) {
 // bytes per row of each operand of an operation
 struct OpDesc { int op; int a_bytes, b_bytes, out_bytes; bool status; size_t chunk_rows; };
 
-// rows per pipeline chunk of the variable-base DH ops: a whole number of k_dh_ladder waves (2 CTAs x 128 rows per SM) keeps
-// the tail of each chunk short; FQ_DH_CHUNK_ROWS overrides it (tuning knob, read once).
+// rows per full pipeline chunk of the variable-base DH ops: a whole number of waves of k_dh_ladder (2 CTAs x 128 rows per SM)
+// and of k_dh_prep (3 per SM) keeps the tail of each chunk short; FQ_DH_CHUNK_ROWS overrides it (tuning knob, read once).
 size_t dh_chunk_rows() {
   static size_t v = 0;
   if (v == 0) {
     const char* e = getenv("FQ_DH_CHUNK_ROWS");
     long long x = e ? atoll(e) : 0;
-    v = x >= 128 ? (size_t)x : (size_t)1 << 17;
+    v = x >= 128 ? (size_t)x : (size_t)148 * 2 * 128 * 12;      // 454,656 rows = 12 waves of k_dh_ladder, 8 of k_dh_prep
   }
   return v;
 }
@@ -186,18 +186,21 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* 
 
   size_t per = (n + ndev - 1) / ndev;
   std::vector<ChunkEv> evs;
-  // Chunk schedule of one slice (the same for every device): ramp up from chunk/8 so that the first kernels start after
-  // a short copy, full chunks in the middle, ramp down so that little work and a short copy-back remain exposed at the
-  // end.  Small batches (<= one chunk) are not split.
+  // Chunk schedule of one slice (the same for every device): ramp up from a small chunk (doubling) so that the first kernels
+  // start after a short copy, full chunks in the middle, ramp down by halves so that little work and a short copy-back remain
+  // exposed at the end.  Batches of at most two small chunks are not split.
   std::vector<size_t> bounds;                        // chunk c covers [bounds[c], bounds[c+1]) of the slice
   {
-    const size_t full = d.chunk_rows, small = full / 8 >= 4096 ? full / 8 : full;
-    size_t pos = 0, sz = (per > full && ramp_enabled()) ? small : full;
+    const size_t full = d.chunk_rows;
+    size_t small = full / 8 >= 16384 ? full / 8 : 16384;
+    if (small > full) small = full;
+    const bool ramp = ramp_enabled() && per > 2 * small;
+    size_t pos = 0, sz = ramp ? small : full;
     bounds.push_back(0);
     while (pos < per) {
       size_t left = per - pos;
       size_t take = sz < left ? sz : left;
-      if (ramp_enabled() && per > full && left > small && left <= 2 * take) take = (left / 2 + 127) / 128 * 128;   // ramp down by halves
+      if (ramp && left > small && left <= 2 * take) take = (left / 2 + 127) / 128 * 128;   // ramp down by halves
       pos += take; bounds.push_back(pos);
       if (sz < full) sz = sz * 2 < full ? sz * 2 : full;
     }
