@@ -342,7 +342,7 @@ def test_ragged_and_empty_batches(fq):
     assert fq.MUL_base(np.zeros((0, 32), np.uint8)).shape == (0, 32)
     out, st = fq.DH(np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8))
     assert out.shape == (0, 32) and st.shape == (0,)
-    k = rng.integers(0, 256, ((1 << 17) + 131, 32), np.uint8)            # crosses a chunk boundary, not a multiple of 128
+    k = rng.integers(0, 256, ((1 << 17) + 131, 32), np.uint8)            # crosses chunk boundaries of the ramped schedule, not a multiple of 128
     full = fq.MUL_base(k)
     for n in (1, 31, 127, 129, 1000):
         assert (fq.MUL_base(k[:n]) == full[:n]).all()
@@ -398,7 +398,7 @@ def test_device_resident_batch_larger_than_one_launch_group(fq):
     do = fqdev.DeviceBuffer(0, n * 32); ds = fqdev.DeviceBuffer(0, n)
     fqdev.dev_run("dh_endo", 0, dk, dp, do, ds, n)
     got, st = do.to_host((n, 32)), ds.to_host((n,))
-    want, wst = fq.DH(k, pub)                                   # host path: chunks of 2^17 rows
+    want, wst = fq.DH(k, pub)                                   # host path: ramped chunks of up to 454,656 rows
     assert not st.any() and not wst.any() and (got == want).all()
     dko = fqdev.DeviceBuffer(0, n * 32)
     fqdev.dev_run("mul_base_comb", 0, dk, None, dko, None, n)
