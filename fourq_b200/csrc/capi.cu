@@ -128,6 +128,7 @@ OpDesc describe(int op) {
     case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT: return {op, 16, 0, 16, false, (size_t)1 << 18};
     case FQ_DEVOP_DECODE: case FQ_DEVOP_DECODE_SPEC: return {op, 32, 0, 64, true, (size_t)1 << 18};
     case FQ_DEVOP_ENCODE: return {op, 64, 0, 32, false, (size_t)1 << 20};
+    case FQ_DEVOP_ON_CURVE: return {op, 64, 0, 1, false, (size_t)1 << 20};
     case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, 32, 32, 32, true, dh_chunk_rows()};
     case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, dh_chunk_rows()};
     case FQ_DEVOP_DH_BASE: case FQ_DEVOP_DH_ENDO_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
@@ -158,6 +159,7 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_DECODE: return fqk_decode(0, a, out, status, n, s);
     case FQ_DEVOP_DECODE_SPEC: return fqk_decode(1, a, out, status, n, s);
     case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
+    case FQ_DEVOP_ON_CURVE: return fqk_on_curve(a, out, n, s);
     case FQ_DEVOP_DH: return fqk_dh(0, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, strict_mode(), a, out, status, n, s);
@@ -298,6 +300,7 @@ int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n,
   return run_host(FQ_DEVOP_FP_BASE + op, a, b, out, nullptr, n, ndev);
 }
 int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE, enc, nullptr, xy, status, n, ndev); }
+int fq_point_on_curve(const uint8_t* xy, uint8_t* ok, size_t n, int ndev) { return run_host(FQ_DEVOP_ON_CURVE, xy, nullptr, ok, nullptr, n, ndev); }
 int fq_decode_spec(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE_SPEC, enc, nullptr, xy, status, n, ndev); }
 int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev) { return run_host(FQ_DEVOP_ENCODE, xy, nullptr, enc, nullptr, n, ndev); }
 int fq_dh(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH, k, enc_pt, enc_out, status, n, ndev); }

@@ -67,6 +67,16 @@ template <bool SPEC> __global__ void __launch_bounds__(256) k_decode(const void*
   st8(xy, 2 * row, wo); st8(xy, 2 * row + 1, wo + 8);
 }
 
+// PointOnCurve (curve4q.py:23-29) on affine rows x | y (any 128-bit halves, reduced mod p): ok[row] = 1 if on the curve
+__global__ void __launch_bounds__(256) k_on_curve(const void* xy, unsigned char* ok, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wi[16];
+  ld8(xy, 2 * row, wi); ld8(xy, 2 * row + 1, wi + 8);
+  fp2 x = fp2_canon(row_load_fp2(wi)), y = fp2_canon(row_load_fp2(wi + 8));
+  ok[row] = pt_on_curve(x, y) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_t n) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
@@ -172,6 +182,11 @@ cudaError_t fqk_decode(int spec, const void* enc, void* xy, void* status, size_t
   if (n == 0) return cudaSuccess;
   if (spec) k_decode<true><<<grid_for(n, 256), 256, 0, s>>>(enc, xy, (unsigned char*)status, n);
   else k_decode<false><<<grid_for(n, 256), 256, 0, s>>>(enc, xy, (unsigned char*)status, n);
+  return cudaGetLastError();
+}
+cudaError_t fqk_on_curve(const void* xy, void* ok, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_on_curve<<<grid_for(n, 256), 256, 0, s>>>(xy, (unsigned char*)ok, n);
   return cudaGetLastError();
 }
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s) {

@@ -10,6 +10,7 @@ cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n
 cudaError_t fqk_fp_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);   // GF(p), 16-byte rows, op = FQ_FP_* of the header
 cudaError_t fqk_decode(int spec, const void* enc, void* xy, void* status, size_t n, cudaStream_t s);   // spec: draft's t == 0 branch instead of the reference's exception
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s);
+cudaError_t fqk_on_curve(const void* xy, void* ok, size_t n, cudaStream_t s);
 // `strict` (everywhere below): table selection by the strict scan instead of masked loads (dh.cuh, fq_set_select_mode)
 // variable-base DH = three kernels (prepare, ladder, finish; kernels_dh.cuh) that hand the per-row table and the projective
 // result over through `scratch`, a device buffer of at least fqk_dh_scratch_bytes(n) bytes owned by the caller.

@@ -1,6 +1,7 @@
 """Batched Curve4Q -- the counterpart of the reference's impl/curve4q.py entry points.
 
     reference (one element, Python ints)            here (N rows, numpy uint8)
+    PointOnCurve((X, Y)) -> bool       :23-29       PointOnCurve(XY[N,64]) -> bool[N]
     encode(X, Y) -> bytearray(32)      :41-46       encode(XY[N,64]) -> B[N,32]
     decode(B) -> (x, y) or raises      :49-96       decode(B[N,32]) -> (XY[N,64], status[N])
     DH_windowed(m, P) -> affine Q      :464-465     DH_windowed(k[N,32], XY[N,64]) -> (XY[N,64], status[N])
@@ -79,6 +80,14 @@ def encode(XY, ndev=1, out=None):
     out = _buf(out, (XY.shape[0], 32), "out")
     _lib.check(_lib.lib().fq_encode(_lib.ptr(XY), _lib.ptr(out), XY.shape[0], ndev))
     return out
+
+
+def PointOnCurve(XY, ndev=1):
+    """curve4q.py:23-29 for N affine points x | y: a (N,) bool array."""
+    XY = _lib.rows(XY, 64, "XY")
+    ok = np.empty((XY.shape[0],), np.uint8)
+    _lib.check(_lib.lib().fq_point_on_curve(_lib.ptr(XY), _lib.ptr(ok), XY.shape[0], ndev))
+    return ok.astype(bool)
 
 
 def decode(B, ndev=1, strict=False, out=None, status=None, spec=False):

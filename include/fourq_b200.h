@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 105
+#define FQ_VERSION 106
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -95,6 +95,8 @@ FQ_API int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, si
  * Unlike the reference, decode does not modify its input. */
 FQ_API int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev);
 FQ_API int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev);
+/* curve4q.py PointOnCurve :23-29 on affine rows x | y (n,64): ok[i] = 1 if -x^2 + y^2 == 1 + d x^2 y^2, else 0 */
+FQ_API int fq_point_on_curve(const uint8_t* xy, uint8_t* ok, size_t n, int ndev);
 /* Opt-in, NOT bit-compatible with the reference on four inputs: decode as the draft specifies it (draft-ladd-cfrg-4q.md:841-888).
  * The reference raises AttributeError when t == 0 (curve4q.py:76-77, status 3 above); the draft continues with
  * t = 2 (t0 - t3), which decodes the encodings of the low-order points (0, 1), (0, -1), (i, 0), (-i, 0).  Every other input
@@ -146,6 +148,7 @@ FQ_API int fq_host_free(void* p);
 #define FQ_DEVOP_FP_BASE 32    /* FQ_DEVOP_FP_BASE + FQ_FP_*: GF(p) ops on 16-byte rows, a (, b), out */
 #define FQ_DEVOP_DECODE 16     /* a = enc, out = xy, status */
 #define FQ_DEVOP_ENCODE 17     /* a = xy, out = enc */
+#define FQ_DEVOP_ON_CURVE 30      /* a = xy, out = ok (1 byte per row) */
 #define FQ_DEVOP_DECODE_SPEC 29   /* as FQ_DEVOP_DECODE with the draft's t == 0 branch (fq_decode_spec) */
 #define FQ_DEVOP_DH 18         /* a = k, b = enc_pt, out, status */
 #define FQ_DEVOP_DH_AFFINE 19  /* a = k, b = xy, out = xy, status */

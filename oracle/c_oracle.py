@@ -29,6 +29,7 @@ def lib():
         L.fqo_dh_base_batch.argtypes = [vp, vp, vp, sz]; L.fqo_dh_base_batch.restype = None
         L.fqo_decode_batch.argtypes = [vp, vp, vp, sz]; L.fqo_decode_batch.restype = None
         L.fqo_encode_batch.argtypes = [vp, vp, sz]; L.fqo_encode_batch.restype = None
+        L.fqo_on_curve_batch.argtypes = [vp, vp, sz]; L.fqo_on_curve_batch.restype = None
         L.fqo_fp2_batch.argtypes = [i, vp, vp, vp, sz]; L.fqo_fp2_batch.restype = i
         L.fqo_fp_batch.argtypes = [i, vp, vp, vp, sz]; L.fqo_fp_batch.restype = i
         _lib = L
@@ -106,6 +107,13 @@ def encode(xy):
     out = np.zeros((xy.shape[0], 32), np.uint8)
     lib().fqo_encode_batch(_p(xy), _p(out), xy.shape[0])
     return out
+
+
+def on_curve(xy):
+    xy = _arr(xy, 64)
+    ok = np.zeros(xy.shape[0], np.uint8)
+    lib().fqo_on_curve_batch(_p(xy), _p(ok), xy.shape[0])
+    return ok.astype(bool)
 
 
 FP2_OPS = {"mul": 0, "sqr": 1, "inv": 2, "add": 3, "sub": 4, "neg": 5, "conj": 6}

@@ -286,6 +286,14 @@ void fqo_dh_base_batch(const uint8_t* k, uint8_t* out, uint8_t* status, size_t n
   encode(GX, GY, genc);
   for (size_t i = 0; i < n; i++) status[i] = (uint8_t)fqo_dh(k + 32 * i, genc, out + 32 * i);
 }
+/* fq_point_on_curve */
+void fqo_on_curve_batch(const uint8_t* xy, uint8_t* ok, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t* b = xy + 64 * i;
+    f2 x = {fp_red(ld128(b)), fp_red(ld128(b + 16))}, y = {fp_red(ld128(b + 32)), fp_red(ld128(b + 48))};
+    ok[i] = (uint8_t)on_curve(x, y);
+  }
+}
 /* fq_decode / fq_encode */
 void fqo_decode_batch(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n) {
   for (size_t i = 0; i < n; i++) {

@@ -116,6 +116,19 @@ def test_strict_select_mode_gives_identical_outputs(fq):
     assert (ref["dh_endo"][0] == want).all() and (ref["dh_endo"][1] == wst).all()
 
 
+def test_point_on_curve(fq, golden):
+    from oracle import c_oracle as C
+    import fourq_b200.curve4q as c4
+    rng = np.random.default_rng(81)
+    pub = fq.MUL_base(rng.integers(0, 256, (5000, 32), np.uint8))
+    xy, st = fq.decode(pub)
+    assert not st.any() and c4.PointOnCurve(xy).all()
+    mixed = xy.copy(); mixed[::3, rng.integers(0, 64)] ^= 0x10
+    mixed = np.concatenate([mixed, rng.integers(0, 256, (999, 64), np.uint8), np.zeros((1, 64), np.uint8)])    # non-canonical halves too
+    got = c4.PointOnCurve(mixed)
+    assert (got == C.on_curve(mixed)).all() and got.any() and not got.all()
+
+
 def test_decode_spec_opt_in(fq, golden):
     rows = golden["codec"]["decode"]
     low = [O.encode(x, y) for x, y in (((0, 0), (1, 0)), ((0, 0), (O.P127 - 1, 0)), ((0, 1), (0, 0)), ((0, O.P127 - 1), (0, 0)))]

@@ -45,6 +45,15 @@ def test_codec_golden(golden):
     assert set(int(s) for s in st) == {0, 1, 2, 3, 4}
 
 
+def test_on_curve(golden):
+    xy = R([H(r[2]) for r in golden["codec"]["decode"] if r[1] == 0])
+    assert C.on_curve(xy).all()
+    bad = xy.copy(); bad[:, 3] ^= 1
+    assert not C.on_curve(bad).any()
+    for j in range(0, len(xy), 16):
+        assert O.on_curve(O.xy_from_bytes(bytes(bad[j]))) is False and O.on_curve(O.xy_from_bytes(bytes(xy[j]))) is True
+
+
 def test_scalar_mult_golden(golden):
     m = golden["mul"]
     rows = m["dh"]
