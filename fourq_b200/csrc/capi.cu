@@ -208,37 +208,41 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* 
     }
   }
   size_t max_chunks = bounds.size() - 1;
+  // one chunk of one device: copies in, kernels, copies out on the chunk's stream.  A failing call returns its error from the
+  // lambda; the caller then stops enqueueing and still waits for and cleans up everything that is already in flight.
+  auto enqueue = [&](size_t c, int i) -> int {
+    size_t lo = (size_t)i * per, hi = lo + per < n ? lo + per : n;
+    size_t r0 = lo + bounds[c];
+    if (lo >= n || r0 >= hi) return FQ_OK;
+    size_t r1 = lo + bounds[c + 1] < hi ? lo + bounds[c + 1] : hi;
+    size_t rows = r1 - r0;
+    int dev = g_dev_base + i, e;
+    if ((e = ctx_init(dev)) != FQ_OK) return e;
+    DevCtx& cx = g_ctx[dev];
+    int si = (int)(c % kStreams);
+    Slot& s = cx.slot[si];
+    cudaStream_t st = cx.st[si];
+    if ((e = slot_reserve(s, 0, d.chunk_rows * d.a_bytes)) != FQ_OK) return e;
+    if (d.b_bytes && (e = slot_reserve(s, 1, d.chunk_rows * d.b_bytes)) != FQ_OK) return e;
+    if ((e = slot_reserve(s, 2, d.chunk_rows * d.out_bytes)) != FQ_OK) return e;
+    if (d.status && (e = slot_reserve(s, 3, d.chunk_rows)) != FQ_OK) return e;
+    if (needs_scratch(op) && (e = dh_scratch_reserve(cx, si, op, d.chunk_rows)) != FQ_OK) return e;
+    CU(cudaMemcpyAsync(s.buf[0], a + r0 * d.a_bytes, rows * d.a_bytes, cudaMemcpyHostToDevice, st));
+    if (d.b_bytes) CU(cudaMemcpyAsync(s.buf[1], b + r0 * d.b_bytes, rows * d.b_bytes, cudaMemcpyHostToDevice, st));
+    ChunkEv ev; ev.dev = i;
+    CU(cudaEventCreate(&ev.e0));
+    if (cudaEventCreate(&ev.e1) != cudaSuccess) { cudaEventDestroy(ev.e0); return fail(FQ_ERR_CUDA, "cudaEventCreate failed"); }
+    evs.push_back(ev);                               // from here on the events are destroyed by the common cleanup
+    CU(cudaEventRecord(ev.e0, st));
+    CU(launch(cx, op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st, si));
+    CU(cudaEventRecord(ev.e1, st));
+    CU(cudaMemcpyAsync(out + r0 * d.out_bytes, s.buf[2], rows * d.out_bytes, cudaMemcpyDeviceToHost, st));
+    if (d.status) CU(cudaMemcpyAsync(status + r0, s.buf[3], rows, cudaMemcpyDeviceToHost, st));
+    return FQ_OK;
+  };
   int rc = FQ_OK;
-  for (size_t c = 0; c < max_chunks && rc == FQ_OK; c++) {
-    for (int i = 0; i < ndev && rc == FQ_OK; i++) {
-      size_t lo = (size_t)i * per, hi = lo + per < n ? lo + per : n;
-      size_t r0 = lo + bounds[c];
-      if (lo >= n || r0 >= hi) continue;
-      size_t r1 = lo + bounds[c + 1] < hi ? lo + bounds[c + 1] : hi;
-      size_t rows = r1 - r0;
-      int dev = g_dev_base + i;
-      if ((rc = ctx_init(dev)) != FQ_OK) break;
-      DevCtx& cx = g_ctx[dev];
-      int si = (int)(c % kStreams);
-      Slot& s = cx.slot[si];
-      cudaStream_t st = cx.st[si];
-      if ((rc = slot_reserve(s, 0, d.chunk_rows * d.a_bytes)) != FQ_OK) break;
-      if (d.b_bytes && (rc = slot_reserve(s, 1, d.chunk_rows * d.b_bytes)) != FQ_OK) break;
-      if ((rc = slot_reserve(s, 2, d.chunk_rows * d.out_bytes)) != FQ_OK) break;
-      if (d.status && (rc = slot_reserve(s, 3, d.chunk_rows)) != FQ_OK) break;
-      if (needs_scratch(op) && (rc = dh_scratch_reserve(cx, si, op, d.chunk_rows)) != FQ_OK) break;
-      CU(cudaMemcpyAsync(s.buf[0], a + r0 * d.a_bytes, rows * d.a_bytes, cudaMemcpyHostToDevice, st));
-      if (d.b_bytes) CU(cudaMemcpyAsync(s.buf[1], b + r0 * d.b_bytes, rows * d.b_bytes, cudaMemcpyHostToDevice, st));
-      ChunkEv ev; ev.dev = i;
-      CU(cudaEventCreate(&ev.e0)); CU(cudaEventCreate(&ev.e1));
-      CU(cudaEventRecord(ev.e0, st));
-      CU(launch(cx, op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st, si));
-      CU(cudaEventRecord(ev.e1, st));
-      evs.push_back(ev);
-      CU(cudaMemcpyAsync(out + r0 * d.out_bytes, s.buf[2], rows * d.out_bytes, cudaMemcpyDeviceToHost, st));
-      if (d.status) CU(cudaMemcpyAsync(status + r0, s.buf[3], rows, cudaMemcpyDeviceToHost, st));
-    }
-  }
+  for (size_t c = 0; c < max_chunks && rc == FQ_OK; c++)
+    for (int i = 0; i < ndev && rc == FQ_OK; i++) rc = enqueue(c, i);
   // wait for every device, then collect kernel times
   for (int i = 0; i < ndev; i++) {
     int dev = g_dev_base + i;
