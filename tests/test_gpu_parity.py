@@ -452,4 +452,11 @@ def test_multi_gpu_slices_match_single(fq):
         pytest.skip("needs 2 GPUs")
     rng = np.random.default_rng(9)
     k = rng.integers(0, 256, (100001, 32), np.uint8)
-    assert (fq.MUL_base(k, ndev=2) == fq.MUL_base(k, ndev=1)).all()
+    pub = fq.MUL_base(k, ndev=1)
+    assert (fq.MUL_base(k, ndev=2) == pub).all()
+    pub[::101] = rng.integers(0, 256, (len(pub[::101]), 32), np.uint8)
+    k2 = rng.integers(0, 256, (100001, 32), np.uint8)
+    o1, s1 = fq.DH(k2, pub, ndev=1)
+    for g in range(2, min(fq.device_count(), 8) + 1):
+        og, sg = fq.DH(k2, pub, ndev=g)                      # contiguous slices of ceil(n/g) rows, ragged last slice
+        assert (og == o1).all() and (sg == s1).all(), g
