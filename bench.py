@@ -316,6 +316,9 @@ def main():
                     "frac": ladder_achieved / wide_peak, "traffic": traffic,
                     "kernel_ms": {"k_dh_prep": ph[0], "k_dh_ladder": ph[1], "k_dh_finish": ph[2]},
                     "step": {"achieved": step_achieved / 1e12, "frac": step_achieved / wide_peak, "imads_per_row": imads},
+                    "hbm": {"achieved": (value / world) * (BYTES_PER_ROW + 2 * 1156) / 1e9, "peak": hbm, "unit": "GB/s",
+                            "frac": (value / world) * (BYTES_PER_ROW + 2 * 1156) / 1e9 / hbm,
+                            "note": "all three kernels: 96 B of inputs/outputs + 1,156 B of scratch written and read once per row; not the bound"},
                     "note": "per GPU; dominant kernel k_dh_ladder: achieved = rows x %d algorithmic 32x32->64 multiply-adds per row of the main loop "
                             "/ its CUDA-event time; step = all three kernels, rows/s x %d (SURVEY 8d, tight count of decode + DH + encode); peak = "
                             "IMAD.WIDE.U32 issue rate measured live by fq_imad_peak (32-bit IMAD measured %.2f T/s); HBM is not the bound: "
