@@ -206,6 +206,28 @@ def test_x25519_golden_and_rfc(fq, golden):
     assert bytes(k[0]).hex() == "684cf59ba83309552800ef566f2f4d3c1c3887c49360e3875f2eb94d99532c51"
 
 
+def _oracle_x25519(args):
+    return O.x25519(args[0], args[1])
+
+
+def test_x25519_random_and_special_vs_oracle(fq):
+    """Config 5's X25519 kernel on 2,048 random (k, u) rows and on special u coordinates (0, 1, p-1, p, p+1, 2^255-1, the
+    low-order points of RFC 7748 section 6 notes, all-ones limbs) x special scalars, against the Python oracle."""
+    rng = np.random.default_rng(91)
+    p = (1 << 255) - 19
+    us = [0, 1, 2, 9, p - 1, p, p + 1, (1 << 255) - 1, (1 << 256) - 1, 1 << 255, (1 << 254) + 7,
+          325606250916557431795983626356110631294008115727848805560023387167927233504,          # order 8
+          39382357235489614581723060781553021112529911719440698176882885853963445705823,        # order 8
+          int("ffffffff00000000" * 4, 16), int("00000000ffffffff" * 4, 16)]
+    ks = [0, 1, 8, (1 << 254), (1 << 255) - 1, (1 << 256) - 1, int("a5" * 32, 16), int("0f" * 32, 16)]
+    kk = [int(a).to_bytes(32, "little") for a in ks for _ in us] + [bytes(r) for r in rng.integers(0, 256, (2048, 32), np.uint8)]
+    uu = [int(b).to_bytes(32, "little") for _ in ks for b in us] + [bytes(r) for r in rng.integers(0, 256, (2048, 32), np.uint8)]
+    got = fq.x25519(R(kk), R(uu))
+    with _pool() as pool:
+        want = pool.map(_oracle_x25519, list(zip(kk, uu)), chunksize=32)
+    assert [bytes(r) for r in got] == want
+
+
 # ---------------------------------------------------------------- seeded random vs the oracle
 
 def _oracle_fp2(args):
