@@ -287,3 +287,19 @@ def test_adversarial_grid_vs_c_oracle(sim):
         out = np.zeros((n, 32), np.uint8); st = np.zeros(n, np.uint8)
         assert getattr(sim, fn)(_p(k), _p(enc), _p(out), _p(st), ctypes.c_size_t(n)) == 0
         assert (st == wst).all() and (out == want).all(), fn
+
+
+def test_x25519_special_values_vs_oracle(sim):
+    """The device X25519 code (simulation) on special u coordinates x special scalars and 200 random rows vs the oracle."""
+    rng = random.Random(91)
+    p = (1 << 255) - 19
+    us = [0, 1, 2, 9, p - 1, p, p + 1, (1 << 255) - 1, (1 << 256) - 1, 1 << 255, (1 << 254) + 7,
+          325606250916557431795983626356110631294008115727848805560023387167927233504,
+          39382357235489614581723060781553021112529911719440698176882885853963445705823,
+          int("ffffffff00000000" * 4, 16), int("00000000ffffffff" * 4, 16)]
+    ks = [0, 1, 8, (1 << 254), (1 << 255) - 1, (1 << 256) - 1, int("a5" * 32, 16), int("0f" * 32, 16)]
+    kk = [int(a).to_bytes(32, "little") for a in ks for _ in us] + [rng.getrandbits(256).to_bytes(32, "little") for _ in range(200)]
+    uu = [int(b).to_bytes(32, "little") for _ in ks for b in us] + [rng.getrandbits(256).to_bytes(32, "little") for _ in range(200)]
+    k = _rows(kk); u = _rows(uu); out = np.zeros(32 * len(kk), np.uint8)
+    sim.sim_x25519(_p(k), _p(u), _p(out), ctypes.c_size_t(len(kk)))
+    assert [bytes(out[32 * i:32 * i + 32]) for i in range(len(kk))] == [O.x25519(a, b) for a, b in zip(kk, uu)]
