@@ -37,7 +37,7 @@ def lib():
     vp, sz, i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     sigs = {
         "fq_version": ([], i), "fq_device_count": ([], i), "fq_last_error": ([], ctypes.c_char_p),
-        "fq_set_device_base": ([i], i), "fq_set_select_mode": ([i], i), "fq_get_select_mode": ([], i), "fq_last_kernel_ms": ([], ctypes.c_float),
+        "fq_set_device_base": ([i], i), "fq_set_select_mode": ([i], i), "fq_get_select_mode": ([], i), "fq_trim": ([], i), "fq_last_kernel_ms": ([], ctypes.c_float),
         "fq_fp2_mul": ([vp, vp, vp, sz, i], i), "fq_fp2_add": ([vp, vp, vp, sz, i], i), "fq_fp2_sub": ([vp, vp, vp, sz, i], i),
         "fq_fp2_sqr": ([vp, vp, sz, i], i), "fq_fp2_inv": ([vp, vp, sz, i], i), "fq_fp2_neg": ([vp, vp, sz, i], i),
         "fq_fp2_conj": ([vp, vp, sz, i], i),
@@ -63,7 +63,7 @@ def lib():
     return L
 
 
-EXPORTS = ["fq_version", "fq_device_count", "fq_last_error", "fq_set_device_base", "fq_set_select_mode", "fq_get_select_mode", "fq_last_kernel_ms", "fq_fp2_mul",
+EXPORTS = ["fq_version", "fq_device_count", "fq_last_error", "fq_set_device_base", "fq_set_select_mode", "fq_get_select_mode", "fq_trim", "fq_last_kernel_ms", "fq_fp2_mul",
            "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_fp_op", "fq_decode", "fq_decode_spec", "fq_encode", "fq_point_on_curve",
            "fq_dh", "fq_dh_affine", "fq_dh_base", "fq_mul_base", "fq_dh_endo", "fq_dh_endo_affine", "fq_dh_endo_base",
            "fq_mul_endo_base", "fq_dh_base_comb", "fq_mul_base_comb", "fq_x25519", "fq_host_alloc", "fq_host_free",

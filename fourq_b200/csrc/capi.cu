@@ -332,6 +332,28 @@ int fq_set_device_base(int first) {
   return FQ_OK;
 }
 
+int fq_trim(void) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int count = device_count();
+  if (count < 0) return count;
+  for (int dev = 0; dev < count && dev < kMaxDev; dev++) {
+    DevCtx& c = g_ctx[dev];
+    if (!c.ready) continue;
+    CU(cudaSetDevice(dev));
+    CU(cudaDeviceSynchronize());
+    for (int si = 0; si < kStreams; si++) {
+      Slot& s = c.slot[si];
+      for (int w = 0; w < 4; w++) {
+        if (s.buf[w]) { CU(cudaFree(s.buf[w])); s.buf[w] = nullptr; s.cap[w] = 0; }
+        if (s.hbuf[w]) { CU(cudaFreeHost(s.hbuf[w])); s.hbuf[w] = nullptr; s.hcap[w] = 0; }
+      }
+      if (c.dh_scratch[si]) { CU(cudaFree(c.dh_scratch[si])); c.dh_scratch[si] = nullptr; c.dh_scratch_cap[si] = 0; }
+    }
+    if (c.flush) { CU(cudaFree(c.flush)); c.flush = nullptr; }
+  }
+  return FQ_OK;
+}
+
 int fq_set_select_mode(int strict) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (strict != 0 && strict != 1) return fail(FQ_ERR_ARG, "select mode must be 0 (masked loads) or 1 (strict scan)");

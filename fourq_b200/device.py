@@ -30,6 +30,11 @@ def get_select_mode():
     return bool(_lib.lib().fq_get_select_mode())
 
 
+def trim():
+    """Frees the per-GPU staging and scratch buffers kept between calls (they are re-allocated on demand)."""
+    _lib.check(_lib.lib().fq_trim())
+
+
 def last_kernel_ms():
     return float(_lib.lib().fq_last_kernel_ms())
 

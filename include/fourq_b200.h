@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 106
+#define FQ_VERSION 107
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -130,6 +130,10 @@ FQ_API int fq_dh_base_comb(const uint8_t* k, uint8_t* enc_out, uint8_t* status, 
 
 /* ---- X25519 (RFC 7748): impl/curve25519.py:88-91 x25519(k, u) -> 32 bytes; k, u, out are (n,32) */
 FQ_API int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev);
+
+/* Frees the staging and scratch buffers the engine keeps per GPU between calls (up to ~0.5 GB per stream slot for the DH
+ * ops); contexts, streams and the fixed-base tables stay.  The next call allocates what it needs again. */
+FQ_API int fq_trim(void);
 
 /* ---- pinned host memory for zero-staging transfers (optional; any host pointer is accepted above) */
 FQ_API int fq_host_alloc(void** p, size_t bytes);

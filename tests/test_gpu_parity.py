@@ -463,6 +463,33 @@ def test_argument_errors_are_reported_not_swallowed(fq):
     assert _lib.lib().fq_dh(None, None, None, None, 0, 1) == _lib.FQ_OK               # n = 0 touches nothing
 
 
+def test_concurrent_callers_and_trim(fq):
+    """Two Python threads call different entry points at the same time (the engine serialises them); fq_trim releases the
+    buffers and the next call works again with the same results."""
+    import threading
+    rng = np.random.default_rng(95)
+    k = rng.integers(0, 256, (30000, 32), np.uint8)
+    pub = fq.MUL_base(k)
+    want_dh = fq.DH(k, pub)
+    want_mul = fq.MUL_base(k, algorithm="endo")
+    res = {}
+
+    def worker(name, fn):
+        for _ in range(4):
+            res[name] = fn()
+    ts = [threading.Thread(target=worker, args=("dh", lambda: fq.DH(k, pub))),
+          threading.Thread(target=worker, args=("mul", lambda: fq.MUL_base(k, algorithm="endo"))),
+          threading.Thread(target=worker, args=("x", lambda: fq.x25519(k, pub)))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert (res["dh"][0] == want_dh[0]).all() and (res["dh"][1] == want_dh[1]).all() and (res["mul"] == want_mul).all()
+    fq.trim()
+    again = fq.DH(k, pub)
+    assert (again[0] == want_dh[0]).all() and (fq.MUL_base(k) == pub).all()
+
+
 def test_pinned_host_buffers(fq):
     rng = np.random.default_rng(8)
     k = fq.pinned_empty((5000, 32)); k[:] = rng.integers(0, 256, (5000, 32), np.uint8)
