@@ -85,7 +85,7 @@ int slot_reserve(Slot& s, int which, size_t bytes) {
 
 bool is_dh_op(int op) { return op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE || op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE; }
 bool is_comb_op(int op) { return op == FQ_DEVOP_DH_BASE_COMB || op == FQ_DEVOP_MUL_BASE_COMB; }
-bool needs_scratch(int op) { return is_dh_op(op) || is_comb_op(op); }
+bool needs_scratch(int op) { return is_dh_op(op) || is_comb_op(op) || op == FQ_DEVOP_X25519; }
 
 int strict_mode() {
   if (g_strict < 0) { const char* e = getenv("FQ_STRICT_SELECT"); g_strict = (e && e[0] == '1') ? 1 : 0; }
@@ -109,7 +109,7 @@ bool is_pinned(const void* p) {
 
 // grows the kernel scratch of stream slot `si` to what `op` needs for `rows` rows
 int dh_scratch_reserve(DevCtx& c, int si, int op, size_t rows) {
-  size_t bytes = is_comb_op(op) ? fqk_comb_scratch_bytes(rows) : fqk_dh_scratch_bytes(rows);
+  size_t bytes = is_comb_op(op) ? fqk_comb_scratch_bytes(rows) : op == FQ_DEVOP_X25519 ? fqk_x25519_scratch_bytes(rows) : fqk_dh_scratch_bytes(rows);
   if (bytes <= c.dh_scratch_cap[si]) return FQ_OK;
   if (c.dh_scratch[si]) CU(cudaFree(c.dh_scratch[si]));
   c.dh_scratch[si] = nullptr; c.dh_scratch_cap[si] = 0;
@@ -189,7 +189,7 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, strict_mode(), a, out, status, n, s);
     case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, strict_mode(), a, out, nullptr, n, s);
-    case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, s);
+    case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, cx.dh_scratch[si], s);
     default: return cudaErrorInvalidValue;
   }
 }

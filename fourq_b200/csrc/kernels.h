@@ -27,5 +27,6 @@ cudaError_t fqk_fixed_base(int dh, int endo, int strict, const void* k, void* ou
 cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s);
 size_t fqk_comb_scratch_bytes(size_t n);     // device scratch the caller passes to fqk_comb
 cudaError_t fqk_comb(int dh, int strict, const void* tabs, const void* k, void* out, void* status, size_t n, void* scratch, int sms, cudaStream_t s);
-cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, cudaStream_t s);
+size_t fqk_x25519_scratch_bytes(size_t n);     // device scratch the caller passes to fqk_x25519 (x2, z2 of every row)
+cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, void* scratch, cudaStream_t s);
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s);

@@ -165,8 +165,9 @@ FQ_FN f25 f25_canon(f25 r) {
   return r;
 }
 
-// curve25519.py:88-91: k, u, out = 8 little-endian words each
-FQ_FN void row_x25519(const u32* kw, const u32* uw, u32* out) {
+// curve25519.py:17-80 up to (and not including) the final inversion: clamp, mask, 255 ladder steps, final swap.
+// The result is x2 / z2.
+FQ_FN void x25519_ladder(const u32* kw, const u32* uw, f25& x2, f25& z2) {
   u32 k[8];
   FQ_UNROLL
   for (int i = 0; i < 8; i++) k[i] = kw[i];
@@ -175,7 +176,8 @@ FQ_FN void row_x25519(const u32* kw, const u32* uw, u32* out) {
   FQ_UNROLL
   for (int i = 0; i < 8; i++) x1.v[i] = uw[i];
   x1.v[7] &= 0x7fffffffu;                                                    // curve25519.py:27-33
-  f25 x2 = f25_small(1), z2 = f25_small(0), x3 = x1, z3 = f25_small(1);
+  f25 x3 = x1, z3 = f25_small(1);
+  x2 = f25_small(1); z2 = f25_small(0);
   u32 swap = 0;
   FQ_NOUNROLL
   for (int t = 254; t >= 0; t--) {                                           // curve25519.py:51-76
@@ -195,6 +197,12 @@ FQ_FN void row_x25519(const u32* kw, const u32* uw, u32* out) {
   }
   u32 m = 0u - swap;
   f25_cswap(m, x2, x3); f25_cswap(m, z2, z3);                                 // curve25519.py:78-79
+}
+
+// curve25519.py:88-91: k, u, out = 8 little-endian words each
+FQ_FN void row_x25519(const u32* kw, const u32* uw, u32* out) {
+  f25 x2, z2;
+  x25519_ladder(kw, uw, x2, z2);
   f25 r = f25_canon(f25_mul(x2, f25_inv(z2)));                                // curve25519.py:80, 35-39
   FQ_UNROLL
   for (int i = 0; i < 8; i++) out[i] = r.v[i];
