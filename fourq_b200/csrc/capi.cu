@@ -84,7 +84,11 @@ int slot_reserve(Slot& s, int which, size_t bytes) {
 }
 
 bool is_dh_op(int op) { return op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE || op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE; }
-bool is_comb_op(int op) { return op == FQ_DEVOP_DH_BASE_COMB || op == FQ_DEVOP_MUL_BASE_COMB; }
+// fixed-base ops: their kernels hand (X, Y, Z) to k_dh_finish through a small scratch
+bool is_comb_op(int op) {
+  return op == FQ_DEVOP_DH_BASE_COMB || op == FQ_DEVOP_MUL_BASE_COMB || op == FQ_DEVOP_DH_BASE || op == FQ_DEVOP_MUL_BASE ||
+         op == FQ_DEVOP_DH_ENDO_BASE || op == FQ_DEVOP_MUL_ENDO_BASE;
+}
 bool needs_scratch(int op) { return is_dh_op(op) || is_comb_op(op) || op == FQ_DEVOP_X25519; }
 
 int strict_mode() {
@@ -183,12 +187,12 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_ON_CURVE: return fqk_on_curve(a, out, n, s);
     case FQ_DEVOP_DH: return fqk_dh(0, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, strict_mode(), a, out, status, n, s);
-    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, strict_mode(), a, out, nullptr, n, s);
+    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, strict_mode(), a, out, status, n, cx.dh_scratch[si], s);
+    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, strict_mode(), a, out, nullptr, n, cx.dh_scratch[si], s);
     case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
     case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, strict_mode(), a, out, status, n, s);
-    case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, strict_mode(), a, out, nullptr, n, s);
+    case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, strict_mode(), a, out, status, n, cx.dh_scratch[si], s);
+    case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, strict_mode(), a, out, nullptr, n, cx.dh_scratch[si], s);
     case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, cx.dh_scratch[si], s);
     default: return cudaErrorInvalidValue;
   }

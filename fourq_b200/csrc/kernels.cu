@@ -1,7 +1,6 @@
 // kernels.cu -- CUDA kernels for sm_100a.  One thread = one row everywhere; rows are read and written with 128-bit
 // vector accesses (a warp touches 1 KiB contiguous per operand).  The arithmetic lives in rows.cuh and below.
-#include "kernels.h"
-#include "kio.cuh"
+#include "kernels_dh.cuh"
 
 __constant__ u32 c_base_tabs[1024];                 // table_windowed(G) | table_windowed([392]G) | table_endo(G) | table_endo([392]G)
 
@@ -86,10 +85,12 @@ __global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_
   st8(enc, row, wo);
 }
 
-// fixed base: [k]G (DH = false) or [k][392]G with neutral rejection (DH = true).  The CTA copies the 1 KiB table of its base
-// point from the constant bank into shared memory once; the selection then reads it by broadcast (dh.cuh SelectBroadcast).
+// fixed base, the reference's shape: [k]G (DH = false) or [k][392]G (DH = true) by MUL_windowed / MUL_endo on the base point's
+// table.  The CTA copies the 1 KiB table from the constant bank into shared memory once; the selection then reads it by
+// broadcast (dh.cuh SelectBroadcast).  The result stays projective: k_dh_finish (kernels_dh.cuh) normalises four rows per
+// inversion, rejects the neutral point for DH, and encodes.
 template <bool DH, bool ENDO, bool STRICT> __global__ void __launch_bounds__(256)
-k_fixed_base(const void* k, void* out, unsigned char* status, size_t n) {
+k_fixed_base(const void* __restrict__ k, DhScratch sc, size_t n) {
   __shared__ uint4 stab[64];
   if (threadIdx.x < 64) {
     const u32* src = c_base_tabs + (ENDO ? 512 : 0) + (DH ? 256 : 0) + 4 * threadIdx.x;
@@ -98,11 +99,13 @@ k_fixed_base(const void* k, void* out, unsigned char* status, size_t n) {
   __syncthreads();
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
-  u32 wk[8], wo[8];
+  u32 wk[8];
   ld8(k, row, wk);
-  u32 st = row_fixed_base<DH, ENDO, STRICT>(wk, stab, wo);
-  if (status) status[row] = (unsigned char)st;
-  st8(out, row, wo);
+  ptR1 R = row_fixed_base_r1<ENDO, STRICT>(wk, stab);
+  uint4* o = sc.R + row;
+  stq(o, R.X.re); stq(o + sc.npad, R.X.im); stq(o + 2 * sc.npad, R.Y.re); stq(o + 3 * sc.npad, R.Y.im);
+  stq(o + 4 * sc.npad, R.Z.re); stq(o + 5 * sc.npad, R.Z.im);
+  sc.meta[row] = 0;
 }
 
 __global__ void k_build_base_tables(u32* out, uint4* scratch) { row_build_base_tables(out, scratch); }
@@ -205,18 +208,28 @@ cudaError_t fqk_dh(int affine, int endo, int strict, const void* k, const void* 
   if (n == 0) return cudaSuccess;
   return endo ? fqk_dh_endo(affine, strict, k, pt, out, status, n, scratch, s, ev) : fqk_dh_windowed(affine, strict, k, pt, out, status, n, scratch, s, ev);
 }
-template <bool STRICT> static void fixed_base_launch(int dh, int endo, unsigned g, const void* k, void* out, unsigned char* st, size_t n, cudaStream_t s) {
-  if (dh && endo) k_fixed_base<true, true, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
-  else if (dh) k_fixed_base<true, false, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
-  else if (endo) k_fixed_base<false, true, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
-  else k_fixed_base<false, false, STRICT><<<g, 256, 0, s>>>(k, out, st, n);
+template <bool STRICT> static void fixed_base_launch(int dh, int endo, unsigned g, const void* k, DhScratch sc, size_t n, cudaStream_t s) {
+  if (dh && endo) k_fixed_base<true, true, STRICT><<<g, 256, 0, s>>>(k, sc, n);
+  else if (dh) k_fixed_base<true, false, STRICT><<<g, 256, 0, s>>>(k, sc, n);
+  else if (endo) k_fixed_base<false, true, STRICT><<<g, 256, 0, s>>>(k, sc, n);
+  else k_fixed_base<false, false, STRICT><<<g, 256, 0, s>>>(k, sc, n);
 }
-cudaError_t fqk_fixed_base(int dh, int endo, int strict, const void* k, void* out, void* status, size_t n, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  unsigned g = grid_for(n, 256);
-  if (strict) fixed_base_launch<true>(dh, endo, g, k, out, (unsigned char*)status, n, s);
-  else fixed_base_launch<false>(dh, endo, g, k, out, (unsigned char*)status, n, s);
-  return cudaGetLastError();
+// scratch: fqk_comb_scratch_bytes(n) bytes (the same projective hand-over as the comb kernel)
+cudaError_t fqk_fixed_base(int dh, int endo, int strict, const void* k, void* out, void* status, size_t n, void* scratch, cudaStream_t s) {
+  for (size_t r0 = 0; r0 < n; r0 += FQ_DH_MAX_BATCH) {
+    const size_t rows = n - r0 < FQ_DH_MAX_BATCH ? n - r0 : FQ_DH_MAX_BATCH;
+    DhScratch sc = fin_scratch_view(scratch, rows);
+    unsigned g = grid_for(rows, 256);
+    const char* kk = (const char*)k + 32 * r0; char* oo = (char*)out + 32 * r0;
+    unsigned char* st = status ? (unsigned char*)status + r0 : nullptr;
+    if (strict) fixed_base_launch<true>(dh, endo, g, kk, sc, rows, s);
+    else fixed_base_launch<false>(dh, endo, g, kk, sc, rows, s);
+    if (dh) k_dh_finish<false, true><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    else k_dh_finish<false, false><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s) {
   if (variant == 0) k_imad_peak<0><<<blocks, 256, 0, s>>>((u32*)scratch, 0x9e3779b9u, trips);

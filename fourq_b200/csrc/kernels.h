@@ -22,7 +22,7 @@ cudaError_t fqk_dh_windowed_init();
 cudaError_t fqk_dh_endo_init();
 cudaError_t fqk_dh_windowed(int affine, int strict, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev);
 cudaError_t fqk_dh_endo(int affine, int strict, const void* k, const void* pt, void* out, void* status, size_t n, void* scratch, cudaStream_t s, cudaEvent_t* ev);
-cudaError_t fqk_fixed_base(int dh, int endo, int strict, const void* k, void* out, void* status, size_t n, cudaStream_t s);
+cudaError_t fqk_fixed_base(int dh, int endo, int strict, const void* k, void* out, void* status, size_t n, void* scratch, cudaStream_t s);   // scratch: fqk_comb_scratch_bytes(n)
 // fixed-base per-digit tables (kernels_comb.cu): tabs is the device buffer returned by fqk_comb_init
 cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s);
 size_t fqk_comb_scratch_bytes(size_t n);     // device scratch the caller passes to fqk_comb

@@ -116,6 +116,14 @@ template <bool CHECK_NEUTRAL, bool ENDO, bool STRICT = FQ_STRICT_DEFAULT> FQ_FN 
   return st;
 }
 
+// the same multiplication left projective (R1), for the kernels that share k_dh_finish
+template <bool ENDO, bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 row_fixed_base_r1(const u32* k, uint4* tab) {
+  TabView T; T.base = tab; T.stride = 1;
+  if (ENDO) { SelectBroadcast<STRICT> sel; sel.T = T; return mul_endo(row_load_scalar(k), sel); }
+  SelectBroadcast<STRICT> sel; sel.T = T;
+  return mul_windowed(row_load_scalar(k), sel);
+}
+
 // Fixed-base tables: out[0..255] = table_windowed(G) (curve4q.py:582), out[256..511] = table_windowed([392]G)
 // (curve4q.py:758-759), out[512..767] = table_endo(G), out[768..1023] = table_endo([392]G) (curve4q.py:760).  scratch: 56 uint4.
 FQ_FN void row_build_base_tables(u32* out, uint4* scratch) {

@@ -85,7 +85,7 @@ def main():
     k = np.random.default_rng(5).integers(0, 256, (n, 32), np.uint8)
     dk = fqdev.DeviceBuffer.from_host(dev, k); do = fqdev.DeviceBuffer(dev, n * 32)
     ref = None
-    for alg, op, imads in (("comb", "mul_base_comb", 20832 + 1504 // 4 + 5 * 48), ("endo", "mul_endo_base", 64 * 656 + 1504 + 96), ("windowed", "mul_base", 92624)):
+    for alg, op, imads in (("comb", "mul_base_comb", 20832 + 1504 // 4 + 5 * 48), ("endo", "mul_endo_base", 64 * 656 + 1504 // 4 + 5 * 48), ("windowed", "mul_base", 62 * (4 * 272 + 384) + 1504 // 4 + 5 * 48)):
         ms = kernel_ms(op, dev, dk, None, do, None, n, reps=3)
         got = do.to_host((n, 32))
         if ref is None:
