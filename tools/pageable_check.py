@@ -1,5 +1,7 @@
-import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""End-to-end DH rate with page-locked vs ordinary (pageable) numpy arrays.  python tools/pageable_check.py"""
+import os, sys, time, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fourq_b200 as fq
 n = 1 << 20
 rng = np.random.default_rng(1)
