@@ -27,6 +27,11 @@ namespace fqsim { extern thread_local u32 cc; }
 #define FQ_NOUNROLL _Pragma("unroll 1")
 #endif
 
+#ifdef FQ_HOSTSIM
+struct uint4 { u32 x, y, z, w; };
+FQ_FN uint4 make_uint4(u32 x, u32 y, u32 z, u32 w) { uint4 r = {x, y, z, w}; return r; }
+#endif
+
 // Scheduling fence.  ptxas interleaves every independent carry chain it can find; with several multiplications in one
 // basic block it keeps more than the 7 predicate registers' worth of carries in flight and spills them into general
 // registers (P2R / bit set / bit test: ~11 % of the instructions of a point addition).  A warp-level sync is one cheap

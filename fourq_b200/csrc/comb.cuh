@@ -81,20 +81,6 @@ template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 mul_comb(const scal& k, co
   return Q;
 }
 
-// fq_mul_base_comb (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base_comb (true): encode([k][392]G), neutral rejected
-template <bool CHECK_NEUTRAL> FQ_FN u32 row_comb(const u32* k, const u32* tab, u32* out) {
-  scal s;
-  FQ_UNROLL
-  for (int i = 0; i < 8; i++) s.v[i] = k[i];
-  fp2 ox, oy;
-  pt_to_affine(mul_comb(s, tab), ox, oy);
-  u32 st = FQ_ST_OK;
-  if (CHECK_NEUTRAL && (fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one()))) st = FQ_ST_NEUTRAL;   // curve4q.py:459
-  if (st == FQ_ST_OK) pt_encode(ox, oy, out);
-  else { FQ_UNROLL for (int i = 0; i < 8; i++) out[i] = 0; }
-  return st;
-}
-
 // Table construction, one call per (base, digit): out = the 192 words of T_i for B = G (which = 0) or [392]G (which = 1).
 // P = [16^i]B by 4 i doublings, then the odd multiples as in table_windowed (curve4q.py:179-185), each normalised to
 // affine.  Run once per device at context creation (126 threads); also by the CPU simulation in tests/hostsim.

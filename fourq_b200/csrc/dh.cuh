@@ -9,11 +9,6 @@
 #include "codec.cuh"
 #include "scalar.cuh"
 
-#ifdef FQ_HOSTSIM
-struct uint4 { u32 x, y, z, w; };
-FQ_FN uint4 make_uint4(u32 x, u32 y, u32 z, u32 w) { uint4 r = {x, y, z, w}; return r; }
-#endif
-
 // per-thread view of the shared-memory table: quad q of entry e is base[(e*8+q)*stride]
 struct TabView { uint4* base; u32 stride; };
 
@@ -135,11 +130,6 @@ template <bool STRICT = FQ_STRICT_DEFAULT> struct SelectShared {
 // (affine, neutral check).
 struct DhState { ptR2 T7; MulPlan plan; };
 
-FQ_FN u32 dh_finish(const ptR1& R, fp2& ox, fp2& oy) {
-  pt_to_affine(R, ox, oy);
-  bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());      // curve4q.py:459
-  return neutral ? FQ_ST_NEUTRAL : FQ_ST_OK;
-}
 FQ_FN void dh_setup_windowed(const scal& k, const fp2& x, const fp2& y, const TabView& T, DhState& D) {
   ptR1 Q = pt_clear_cofactor(x, y);
   D.T7 = tab_build(T, Q);
@@ -166,11 +156,4 @@ FQ_FN void r2_to_words(const ptR2& P, u32* w) {
   const fp* f[8] = {&P.N.re, &P.N.im, &P.D.re, &P.D.im, &P.E.re, &P.E.im, &P.F.re, &P.F.im};
   FQ_UNROLL
   for (int q = 0; q < 8; q++) { FQ_UNROLL for (int j = 0; j < 4; j++) w[q * 4 + j] = f[q]->v[j]; }
-}
-
-// [k]B for the base point whose table is T; returns canonical affine.  MUL_windowed(k, ., table) + R1toAffine.
-template <bool STRICT = FQ_STRICT_DEFAULT> FQ_FN void mul_fixed_base(const scal& k, const TabView& T, fp2& ox, fp2& oy) {
-  SelectBroadcast<STRICT> sel; sel.T = T;
-  ptR1 R = mul_windowed(k, sel);
-  pt_to_affine(R, ox, oy);
 }

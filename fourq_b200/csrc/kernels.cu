@@ -14,36 +14,14 @@ template <int OP> __global__ void __launch_bounds__(256) k_fp2_op(const void* a,
   st8(out, row, wo);
 }
 
-// GFp2.inv (fields.py:194-199) for FQ_INV_ROWS rows per thread with ONE x^(p-2) chain (Montgomery's trick: prefix products,
-// one inversion, back-substitution: 3 multiplications per row instead of a 138-step chain).  inv(0) = 0 as in the reference:
-// a zero is replaced by 1 inside the shared product and its output forced to 0.  Thread t owns rows t, t + stride, ...
-#define FQ_INV_ROWS 4
-__global__ void __launch_bounds__(128) k_fp2_inv_batched(const void* __restrict__ a, void* __restrict__ out, size_t n) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  fp2 pre[FQ_INV_ROWS], z[FQ_INV_ROWS];
-  u32 zero[FQ_INV_ROWS];
-  fp2 acc = fp2_one();
-#pragma unroll
-  for (int j = 0; j < FQ_INV_ROWS; j++) {
-    const size_t row = t + j * stride;
-    fp2 x = fp2_one();
-    if (row < n) { u32 w[8]; ld8(a, row, w); x = row_load_fp2(w); }
-    zero[j] = (fp_is_zero(x.re) & fp_is_zero(x.im)) ? 0xffffffffu : 0u;
-    x = fp2_select(zero[j], fp2_one(), x);
-    z[j] = x;
-    acc = (j == 0) ? x : fp2_mul_c(acc, x);
-    pre[j] = acc;
-  }
-  fp2 inv = fp2_inv(acc);
-#pragma unroll
-  for (int j = FQ_INV_ROWS - 1; j >= 0; j--) {
-    const size_t row = t + j * stride;
-    fp2 r = (j == 0) ? inv : fp2_mul_c(inv, pre[j > 0 ? j - 1 : 0]);
-    if (j > 0) inv = fp2_mul_c(inv, z[j]);
-    r = fp2_select(zero[j], fp2_zero(), r);
-    if (row < n) { u32 w[8]; row_store_fp2(w, r); st8(out, row, w); }
-  }
+// GFp2.inv (fields.py:194-199) for FQ_BATCHINV_ROWS rows per thread with ONE x^(p-2) chain (batchinv.cuh: 3 multiplications per row
+// instead of a 138-step chain).  inv(0) = 0 as in the reference.  Thread t owns rows t, t + stride, ...; `out` must not alias `a`
+// (the prefix products are parked in it).
+__global__ void __launch_bounds__(64) k_fp2_inv_batched(const void* __restrict__ a, void* __restrict__ out, size_t n) {
+  Fp2InvIO io;
+  io.a = reinterpret_cast<const uint4*>(a); io.out = reinterpret_cast<uint4*>(out); io.n = n;
+  io.stride = (size_t)gridDim.x * blockDim.x; io.t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  batch_invert<Fp2Ops>(io, FQ_BATCHINV_ROWS);
 }
 
 // GF(p) op on 16-byte rows: one 128-bit load per operand and one 128-bit store per thread
@@ -156,7 +134,7 @@ cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n
   switch (op) {
     case FQK_MUL: k_fp2_op<FQ_OP_MUL><<<g, 256, 0, s>>>(a, b, out, n); break;
     case FQK_SQR: k_fp2_op<FQ_OP_SQR><<<g, 256, 0, s>>>(a, b, out, n); break;
-    case FQK_INV: k_fp2_inv_batched<<<grid_for((n + FQ_INV_ROWS - 1) / FQ_INV_ROWS, 128), 128, 0, s>>>(a, out, n); break;
+    case FQK_INV: k_fp2_inv_batched<<<grid_for((n + FQ_BATCHINV_ROWS - 1) / FQ_BATCHINV_ROWS, 64), 64, 0, s>>>(a, out, n); break;
     case FQK_ADD: k_fp2_op<FQ_OP_ADD><<<g, 256, 0, s>>>(a, b, out, n); break;
     case FQK_SUB: k_fp2_op<FQ_OP_SUB><<<g, 256, 0, s>>>(a, b, out, n); break;
     case FQK_NEG: k_fp2_op<FQ_OP_NEG><<<g, 256, 0, s>>>(a, b, out, n); break;
@@ -224,8 +202,8 @@ cudaError_t fqk_fixed_base(int dh, int endo, int strict, const void* k, void* ou
     unsigned char* st = status ? (unsigned char*)status + r0 : nullptr;
     if (strict) fixed_base_launch<true>(dh, endo, g, kk, sc, rows, s);
     else fixed_base_launch<false>(dh, endo, g, kk, sc, rows, s);
-    if (dh) k_dh_finish<false, true><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
-    else k_dh_finish<false, false><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    if (dh) k_dh_finish<false, true><<<dh_finish_grid(rows), FQ_FIN_THREADS, 0, s>>>(sc, oo, st, rows);
+    else k_dh_finish<false, false><<<dh_finish_grid(rows), FQ_FIN_THREADS, 0, s>>>(sc, oo, st, rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(64) k_comb_build(u32* tabs) {
   comb_build_digit(which, i, tabs + which * FQ_COMB_WORDS + i * FQ_COMB_DIGIT_WORDS);
 }
 
-// [k]B in R1 for every row; (X, Y, Z) go to scratch for k_dh_finish (one inversion per FQ_FIN_ROWS rows, encode)
+// [k]B in R1 for every row; (X, Y, Z) go to scratch for k_dh_finish (one inversion per FQ_BATCHINV_ROWS rows, encode)
 template <bool DH, bool STRICT> __global__ void __launch_bounds__(FQ_COMB_THREADS)
 k_comb(const u32* __restrict__ tabs, const void* __restrict__ k, DhScratch sc, size_t n) {
   extern __shared__ uint4 stab4[];
@@ -72,11 +72,11 @@ cudaError_t fqk_comb(int dh, int strict, const void* tabs, const void* k, void* 
     if (dh) {
       if (strict) k_comb<true, true><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
       else k_comb<true, false><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
-      k_dh_finish<false, true><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+      k_dh_finish<false, true><<<dh_finish_grid(rows), FQ_FIN_THREADS, 0, s>>>(sc, oo, st, rows);
     } else {
       if (strict) k_comb<false, true><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
       else k_comb<false, false><<<g, FQ_COMB_THREADS, FQ_COMB_WORDS * 4, s>>>((const u32*)tabs, kk, sc, rows);
-      k_dh_finish<false, false><<<dh_finish_grid(rows), FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+      k_dh_finish<false, false><<<dh_finish_grid(rows), FQ_FIN_THREADS, 0, s>>>(sc, oo, st, rows);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

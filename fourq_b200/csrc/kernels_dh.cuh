@@ -8,49 +8,23 @@
 //   k_dh_ladder  copies the row's table into shared memory ([entry][quad][thread], 112 KiB per CTA, entry 7 in
 //                registers) and runs the 64 x (DBL + ADD) or 62 x (4 DBL + ADD) loop; two CTAs per SM (shared memory
 //                and ~200 registers both allow 256 threads).  Writes (X, Y, Z) to scratch.
-//   k_dh_finish  each thread normalises FQ_FIN_ROWS rows with ONE inversion (Montgomery's trick: prefix products, one
-//                x^(p-2) chain, back-substitution), checks for the neutral point, encodes, writes result and status.
+//   k_dh_finish  each thread normalises FQ_BATCHINV_ROWS rows with ONE inversion (Montgomery's trick: prefix products parked
+//                in the output rows, one x^(p-2) chain, back-substitution), checks for the neutral point, encodes, writes
+//                result and status (batchinv.cuh).
 // All three are bound by integer-instruction issue (IMAD.WIDE.U32 at half rate plus its carry handling); the split lets
 // the setup run with 12 warps per SM instead of 8 and removes 3/4 of the inversions.  The scratch traffic (2.3 KiB per
-// row) is ~3 % of HBM bandwidth at the measured row rate.  k_dh (below) is the same row as ONE kernel; it is kept for
-// A/B experiments (tools/kexp/split.cu) and is not instantiated by the library.
+// row) is ~3 % of HBM bandwidth at the measured row rate.  (The same row as ONE fused kernel lives in tools/kexp/fused_dh.cuh
+// for A/B experiments; it is not part of the library.)
 #pragma once
 #include "kernels.h"
 #include "kio.cuh"
+#include "batchinv.cuh"
 
 #define FQ_DH_THREADS 128
 #define FQ_DH_SMEM (56 * 16 * FQ_DH_THREADS)       // 7 table entries x 8 quads x 16 B per thread = 112 KiB per CTA
 
-template <bool AFFINE, bool ENDO> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
-k_dh(const void* __restrict__ k, const void* __restrict__ pt, void* __restrict__ out, unsigned char* __restrict__ status, size_t n) {
-  extern __shared__ uint4 smem[];
-  TabView T; T.base = smem + threadIdx.x; T.stride = FQ_DH_THREADS;
-  const size_t ntiles = (n + FQ_DH_THREADS - 1) / FQ_DH_THREADS;
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    size_t row = tile * FQ_DH_THREADS + threadIdx.x;
-    const bool live = row < n;
-    if (!live) row = n - 1;                          // tail threads recompute the last row and store nothing
-    DhState D;
-    u32 st;
-    {
-      u32 wk[8], wp[AFFINE ? 16 : 8];
-      ld8(k, row, wk);
-      if (AFFINE) { ld8(pt, 2 * row, wp); ld8(pt, 2 * row + 1, wp + 8); } else ld8(pt, row, wp);
-      st = row_dh_setup<ENDO, AFFINE>(wk, wp, T, D);
-    }
-    ptR1 R = row_dh_loop<ENDO>(T, D);
-    u32 wo[AFFINE ? 16 : 8];
-    st = row_dh_finish<AFFINE>(st, R, wo);
-    if (live) {
-      status[row] = (unsigned char)st;
-      if (AFFINE) { st8(out, 2 * row, wo); st8(out, 2 * row + 1, wo + 8); } else st8(out, row, wo);
-    }
-  }
-}
-
 // ---------------------------------------------------------------- the three-kernel pipeline
 
-#define FQ_FIN_ROWS 4                                // rows per thread that share one inversion in k_dh_finish
 #define FQ_DH_SCRATCH_QUADS (64 + 2 + 6)             // table | digit register | (X, Y, Z), 16 B each
 #define FQ_DH_MAX_BATCH ((size_t)1 << 22)            // rows per launch group (keeps the u32 table indices in range)
 
@@ -109,55 +83,18 @@ k_dh_ladder(DhScratch sc) {
   stq(o + 4 * sc.npad, R.Z.re); stq(o + 5 * sc.npad, R.Z.im);
 }
 
-// R1toAffine (curve4q.py:103-106) for FQ_FIN_ROWS rows of a thread with one GF(p^2) inversion, the neutral check of DH_core
-// (curve4q.py:459), encode (curve4q.py:41-46).  Thread t owns rows t, t + stride, ...  Z is never 0 on the curve (complete
-// formulas); a zero (only possible on rows that already failed validation) is replaced by 1 so it cannot poison the
-// shared product.
-// CHECK_NEUTRAL = false (fq_mul_base_comb): MUL_* has no failure path, the neutral point is encoded like any other and
-// status may be null.
-template <bool AFFINE, bool CHECK_NEUTRAL> __global__ void __launch_bounds__(FQ_DH_THREADS)
+// R1toAffine (curve4q.py:103-106) for FQ_BATCHINV_ROWS rows of a thread with one GF(p^2) inversion, the neutral check of DH_core
+// (curve4q.py:459), encode (curve4q.py:41-46): batchinv.cuh FinishIO.  Thread t owns rows t, t + stride, ...
+#define FQ_FIN_THREADS 64
+template <bool AFFINE, bool CHECK_NEUTRAL> __global__ void __launch_bounds__(FQ_FIN_THREADS)
 k_dh_finish(DhScratch sc, void* __restrict__ out, unsigned char* __restrict__ status, size_t n) {
-  const size_t stride = (size_t)gridDim.x * FQ_DH_THREADS;
-  const size_t t = (size_t)blockIdx.x * FQ_DH_THREADS + threadIdx.x;
-  fp2 pre[FQ_FIN_ROWS];
-  fp2 acc = fp2_one();
-  FQ_UNROLL
-  for (int j = 0; j < FQ_FIN_ROWS; j++) {
-    const size_t row = t + j * stride;
-    fp2 z = fp2_one();
-    if (row < n) { const uint4* o = sc.R + row; z = fp2_set(ldq(o + 4 * sc.npad), ldq(o + 5 * sc.npad)); }
-    if (fp_is_zero(z.re) & fp_is_zero(z.im)) z = fp2_one();
-    acc = (j == 0) ? z : fp2_mul_c(acc, z);
-    pre[j] = acc;
-  }
-  fp2 inv = fp2_inv(acc);
-  FQ_UNROLL
-  for (int j = FQ_FIN_ROWS - 1; j >= 0; j--) {
-    const size_t row = t + j * stride;
-    fp2 z = fp2_one(), X = fp2_zero(), Y = fp2_one();
-    if (row < n) {
-      const uint4* o = sc.R + row;
-      X = fp2_set(ldq(o), ldq(o + sc.npad)); Y = fp2_set(ldq(o + 2 * sc.npad), ldq(o + 3 * sc.npad));
-      z = fp2_set(ldq(o + 4 * sc.npad), ldq(o + 5 * sc.npad));
-    }
-    if (fp_is_zero(z.re) & fp_is_zero(z.im)) z = fp2_one();
-    fp2 zi = (j == 0) ? inv : fp2_mul_c(inv, pre[j > 0 ? j - 1 : 0]);
-    if (j > 0) inv = fp2_mul_c(inv, z);
-    fp2 ox = fp2_canon(fp2_mul_c(X, zi)), oy = fp2_canon(fp2_mul_c(Y, zi));
-    if (row < n) {
-      u32 st = sc.meta[row] >> 8;
-      const bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());      // curve4q.py:459
-      if (CHECK_NEUTRAL && st == FQ_ST_OK && neutral) st = FQ_ST_NEUTRAL;
-      u32 wo[AFFINE ? 16 : 8];
-      if (AFFINE) { if (st == FQ_ST_OK) { row_store_fp2(wo, ox); row_store_fp2(wo + 8, oy); } else row_zero(wo, 16); }
-      else { if (st == FQ_ST_OK) pt_encode(ox, oy, wo); else row_zero(wo, 8); }
-      if (status) status[row] = (unsigned char)st;
-      if (AFFINE) { st8(out, 2 * row, wo); st8(out, 2 * row + 1, wo + 8); } else st8(out, row, wo);
-    }
-  }
+  FinishIO<AFFINE, CHECK_NEUTRAL> io;
+  io.R = sc.R; io.meta = sc.meta; io.npad = sc.npad; io.out = reinterpret_cast<uint4*>(out); io.status = status; io.n = n;
+  io.stride = (size_t)gridDim.x * FQ_FIN_THREADS; io.t = (size_t)blockIdx.x * FQ_FIN_THREADS + threadIdx.x;
+  batch_invert<Fp2Ops>(io, FQ_BATCHINV_ROWS);
 }
 static inline unsigned dh_finish_grid(size_t rows) {
-  return (unsigned)((((rows + FQ_FIN_ROWS - 1) / FQ_FIN_ROWS) + FQ_DH_THREADS - 1) / FQ_DH_THREADS);
+  return (unsigned)((((rows + FQ_BATCHINV_ROWS - 1) / FQ_BATCHINV_ROWS) + FQ_FIN_THREADS - 1) / FQ_FIN_THREADS);
 }
 // scratch of a producer that only hands (X, Y, Z) and a status word to k_dh_finish (the fixed-base comb kernel)
 static inline size_t fin_scratch_bytes(size_t rows) {
@@ -196,8 +133,8 @@ template <bool ENDO> static cudaError_t dh_launch(int affine, int strict, const 
     if (strict) k_dh_ladder<ENDO, true><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(sc);
     else k_dh_ladder<ENDO, false><<<g, FQ_DH_THREADS, FQ_DH_SMEM, s>>>(sc);
     if (ev) cudaEventRecord(ev[2], s);
-    if (affine) k_dh_finish<true, true><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
-    else k_dh_finish<false, true><<<gf, FQ_DH_THREADS, 0, s>>>(sc, oo, st, rows);
+    if (affine) k_dh_finish<true, true><<<gf, FQ_FIN_THREADS, 0, s>>>(sc, oo, st, rows);
+    else k_dh_finish<false, true><<<gf, FQ_FIN_THREADS, 0, s>>>(sc, oo, st, rows);
     if (ev) cudaEventRecord(ev[3], s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

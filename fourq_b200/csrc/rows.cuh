@@ -85,38 +85,9 @@ template <bool ENDO, bool AFFINE> FQ_FN u32 row_dh_setup(const u32* k, const u32
   return st;
 }
 template <bool ENDO, bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 row_dh_loop(const TabView& T, DhState& D) { return ENDO ? dh_loop_endo<STRICT>(T, D) : dh_loop_windowed<STRICT>(T, D); }
-template <bool AFFINE> FQ_FN u32 row_dh_finish(u32 st, const ptR1& R, u32* out) {
-  fp2 ox, oy;
-  u32 st2 = dh_finish(R, ox, oy);
-  if (st == FQ_ST_OK) st = st2;
-  if (AFFINE) { if (st == FQ_ST_OK) { row_store_fp2(out, ox); row_store_fp2(out + 8, oy); } else row_zero(out, 16); }
-  else { if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8); }
-  return st;
-}
-template <bool ENDO> FQ_FN u32 row_dh(const u32* k, const u32* enc, u32* out, const TabView& T) {
-  DhState D;
-  u32 st = row_dh_setup<ENDO, false>(k, enc, T, D);
-  return row_dh_finish<false>(st, row_dh_loop<ENDO>(T, D), out);
-}
-template <bool ENDO> FQ_FN u32 row_dh_affine(const u32* k, const u32* xy, u32* out, const TabView& T) {
-  DhState D;
-  u32 st = row_dh_setup<ENDO, true>(k, xy, T, D);
-  return row_dh_finish<true>(st, row_dh_loop<ENDO>(T, D), out);
-}
-// fq_mul_base (CHECK_NEUTRAL = false): encode([k]G);  fq_dh_base (true): encode([k][392]G) with the neutral check
-// tab: the 64 quads of the base point's table, [entry][quad], in shared memory on the device
-template <bool CHECK_NEUTRAL, bool ENDO, bool STRICT = FQ_STRICT_DEFAULT> FQ_FN u32 row_fixed_base(const u32* k, uint4* tab, u32* out) {
-  fp2 ox, oy;
-  TabView T; T.base = tab; T.stride = 1;
-  if (ENDO) { SelectBroadcast<STRICT> sel; sel.T = T; pt_to_affine(mul_endo(row_load_scalar(k), sel), ox, oy); }
-  else mul_fixed_base<STRICT>(row_load_scalar(k), T, ox, oy);
-  u32 st = FQ_ST_OK;
-  if (CHECK_NEUTRAL && (fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one()))) st = FQ_ST_NEUTRAL;
-  if (st == FQ_ST_OK) pt_encode(ox, oy, out); else row_zero(out, 8);
-  return st;
-}
 
-// the same multiplication left projective (R1), for the kernels that share k_dh_finish
+// fq_mul_base / fq_dh_base and the endo variants: MUL_windowed | MUL_endo on the base point's table (tab: the 64 quads of the
+// table, [entry][quad], in shared memory on the device); the result stays projective (R1) for k_dh_finish
 template <bool ENDO, bool STRICT = FQ_STRICT_DEFAULT> FQ_FN ptR1 row_fixed_base_r1(const u32* k, uint4* tab) {
   TabView T; T.base = tab; T.stride = 1;
   if (ENDO) { SelectBroadcast<STRICT> sel; sel.T = T; return mul_endo(row_load_scalar(k), sel); }

@@ -260,3 +260,53 @@ FQ_FN void row_x25519(const u32* kw, const u32* uw, u32* out) {
   FQ_UNROLL
   for (int i = 0; i < 8; i++) out[i] = r.v[i];
 }
+
+// ---------------------------------------------------------------- shared inversion of the final x2 / z2 (batchinv.cuh)
+// scratch: x2 then z2, each as two quads per row, component-major ([4][npad] uint4)
+FQ_FN void st_f25(uint4* p, size_t npad, const f25& a) {
+  p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); p[npad] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+FQ_FN f25 ld_f25(const uint4* p, size_t npad) {
+  uint4 a = p[0], b = p[npad];
+  f25 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// x2 * z2^(p-2) (curve25519.py:78-80) and the canonical little-endian output (:35-39) for FQ_BATCHINV_ROWS rows per thread
+struct F25Ops {
+  typedef f25 elem;
+  static FQ_MFN f25 one() { return f25_small(1); }
+  static FQ_MFN f25 mul(const f25& a, const f25& b) { return f25_mul(a, b); }
+  static FQ_MFN f25 inv(const f25& a) { return f25_inv(a); }
+};
+struct X25519FinIO {
+  const uint4* scratch; size_t npad; uint4* out; size_t n, t, stride;
+  FQ_MFN f25 z(int j, u32& zero) const {
+    const size_t row = t + (size_t)j * stride;
+    f25 v = f25_small(1);
+    if (row < n) v = ld_f25(scratch + 2 * npad + row, npad);
+    f25 c = f25_canon(v);
+    u32 nz = 0;
+FQ_UNROLL
+    for (int i = 0; i < 8; i++) nz |= c.v[i];
+    zero = nz == 0 ? 0xffffffffu : 0u;
+FQ_UNROLL
+    for (int i = 0; i < 8; i++) v.v[i] = (v.v[i] & ~zero) | ((i == 0 ? 1u : 0u) & zero);
+    return v;
+  }
+  FQ_MFN void park(int j, const f25& acc) const {
+    const size_t row = t + (size_t)j * stride;
+    if (row < n) st_f25(out + 2 * row, 1, acc);
+  }
+  FQ_MFN f25 parked(int j) const {
+    const size_t row = t + (size_t)j * stride;
+    return row < n ? ld_f25(out + 2 * row, 1) : f25_small(1);
+  }
+  FQ_MFN void emit(int j, const f25& zi, u32 zero) const {
+    const size_t row = t + (size_t)j * stride;
+    if (row >= n) return;
+    f25 r = f25_canon(f25_mul(ld_f25(scratch + row, npad), zi));
+    out[2 * row] = make_uint4(r.v[0] & ~zero, r.v[1] & ~zero, r.v[2] & ~zero, r.v[3] & ~zero);
+    out[2 * row + 1] = make_uint4(r.v[4] & ~zero, r.v[5] & ~zero, r.v[6] & ~zero, r.v[7] & ~zero);
+  }
+};

@@ -93,6 +93,29 @@ def test_fp2_random_and_adversarial_vs_oracle(sim):
         assert g == O.row_fp2("inv", a)
 
 
+def test_fp_mul_sqr_random_and_adversarial_vs_ints(sim):
+    """GF(p) mul and the dedicated 10-product squaring (fp.cuh fp_sqr / fp_fold7) against Python ints (fields.py:42-51):
+    edge values, carry-maximising limb patterns (any 128-bit input: the entry point reduces first), 100k random."""
+    rng = random.Random(11)
+    p = O.P127
+    special = [0, 1, 2, p - 1, p, p + 1, p - 2, 1 << 126, (1 << 126) - 1, (1 << 127), (1 << 128) - 1, (1 << 64) - 1, (1 << 64) + 1, (1 << 96) - 1,
+               0xFFFFFFFF, (1 << 127) - (1 << 32), (1 << 127) - (1 << 64) - 1, 0xFFFFFFFF00000000FFFFFFFF00000000, 0x7FFFFFFF00000000FFFFFFFFFFFFFFFF,
+               0x7FFFFFFFFFFFFFFF0000000000000000, 0x7FFFFFFFFFFFFFFFFFFFFFFF00000000, 0x7FFFFFFF000000000000000000000000, 0x7FFFFFFFFFFFFFFF00000000FFFFFFFF]
+    vals = list(special)
+    for _ in range(4096):
+        vals.append(int.from_bytes(bytes(rng.choice([0, 0xFF, 0x80, 0x7F, 0x01]) for _ in range(16)), "little"))
+    vals += [rng.getrandbits(128) for _ in range(100000)]
+    a = _rows([x.to_bytes(16, "little") for x in vals]); out = np.zeros_like(a)
+    assert sim.sim_fp_row_op(FPOPS["sqr"], _p(a), None, _p(out), ctypes.c_size_t(len(vals))) == 0
+    got = [int.from_bytes(bytes(out[16 * i:16 * i + 16]), "little") for i in range(len(vals))]
+    assert got == [x * x % p for x in vals]
+    ys = vals[1:] + vals[:1]
+    b = _rows([y.to_bytes(16, "little") for y in ys])
+    assert sim.sim_fp_row_op(FPOPS["mul"], _p(a), _p(b), _p(out), ctypes.c_size_t(len(vals))) == 0
+    got = [int.from_bytes(bytes(out[16 * i:16 * i + 16]), "little") for i in range(len(vals))]
+    assert got == [x * y % p for x, y in zip(vals, ys)]
+
+
 def test_fp_inv_invsqrt_dbl_half(sim, golden):
     for which, key in ((0, "fp_inv"), (1, "fp_invsqrt")):
         rows = golden["fields"][key]
