@@ -13,9 +13,9 @@ FQ_OK, FQ_ERR_NO_DEVICE, FQ_ERR_CUDA, FQ_ERR_ARG = 0, -1, -2, -3
 # op codes of fq_dev_run (include/fourq_b200.h)
 FPOP = {"mul": 0, "sqr": 1, "inv": 2, "add": 3, "sub": 4, "neg": 5, "invsqrt": 6}      # FQ_FP_* of the header
 DEVOP = {"fp_mul": 32, "fp_sqr": 33, "fp_inv": 34, "fp_add": 35, "fp_sub": 36, "fp_neg": 37, "fp_invsqrt": 38,
-         "fp2_mul": 0, "fp2_sqr": 1, "fp2_inv": 2, "fp2_add": 3, "fp2_sub": 4, "fp2_neg": 5, "fp2_conj": 6,
+         "fp2_mul": 0, "fp2_sqr": 1, "fp2_inv": 2, "fp2_add": 3, "fp2_sub": 4, "fp2_neg": 5, "fp2_conj": 6, "fp2_invsqrt": 7, "fp2_select": 8, "fp_select": 9,
          "decode": 16, "decode_spec": 29, "encode": 17, "dh": 18, "dh_affine": 19, "dh_base": 20, "mul_base": 21, "x25519": 22,
-         "dh_endo": 23, "dh_endo_affine": 24, "dh_endo_base": 25, "mul_endo_base": 26, "dh_base_comb": 27, "mul_base_comb": 28}
+         "dh_endo": 23, "dh_endo_affine": 24, "dh_endo_base": 25, "mul_endo_base": 26, "dh_base_comb": 27, "mul_base_comb": 28, "on_curve": 30}
 
 
 class FourQError(RuntimeError):
@@ -33,14 +33,20 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise FourQError("%s not found: build it with `python -m fourq_b200.build` (needs nvcc). "
                          "fourq_b200 has no CPU implementation." % LIB_PATH)
-    L = ctypes.CDLL(LIB_PATH)
+    _lib = bind(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def bind(L):
+    """Sets the argument and result types of every entry point of include/fourq_b200.h on a loaded library."""
     vp, sz, i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     sigs = {
         "fq_version": ([], i), "fq_device_count": ([], i), "fq_last_error": ([], ctypes.c_char_p),
         "fq_set_device_base": ([i], i), "fq_set_select_mode": ([i], i), "fq_get_select_mode": ([], i), "fq_trim": ([], i), "fq_last_kernel_ms": ([], ctypes.c_float),
         "fq_fp2_mul": ([vp, vp, vp, sz, i], i), "fq_fp2_add": ([vp, vp, vp, sz, i], i), "fq_fp2_sub": ([vp, vp, vp, sz, i], i),
         "fq_fp2_sqr": ([vp, vp, sz, i], i), "fq_fp2_inv": ([vp, vp, sz, i], i), "fq_fp2_neg": ([vp, vp, sz, i], i),
-        "fq_fp2_conj": ([vp, vp, sz, i], i),
+        "fq_fp2_conj": ([vp, vp, sz, i], i), "fq_fp2_invsqrt": ([vp, vp, sz, i], i),
+        "fq_fp_select": ([vp, vp, vp, vp, sz, i], i), "fq_fp2_select": ([vp, vp, vp, vp, sz, i], i),
         "fq_fp_op": ([i, vp, vp, vp, sz, i], i),
         "fq_decode": ([vp, vp, vp, sz, i], i), "fq_decode_spec": ([vp, vp, vp, sz, i], i), "fq_encode": ([vp, vp, sz, i], i), "fq_point_on_curve": ([vp, vp, sz, i], i),
         "fq_dh": ([vp, vp, vp, vp, sz, i], i), "fq_dh_affine": ([vp, vp, vp, vp, sz, i], i),
@@ -53,21 +59,21 @@ def lib():
         "fq_dev_alloc": ([i, ctypes.POINTER(vp), sz], i), "fq_dev_free": ([i, vp], i),
         "fq_dev_upload": ([i, vp, vp, sz], i), "fq_dev_download": ([i, vp, vp, sz], i),
         "fq_dev_run": ([i, i, vp, vp, vp, vp, sz, i, ctypes.POINTER(ctypes.c_float)], i),
+        "fq_dev_run3": ([i, i, vp, vp, vp, vp, vp, sz, i, ctypes.POINTER(ctypes.c_float)], i),
         "fq_dev_flush_l2": ([i], i), "fq_dev_last_phase_ms": ([ctypes.POINTER(ctypes.c_float)], i),
         "fq_imad_peak": ([i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)], i),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(L, name)
         fn.argtypes, fn.restype = argtypes, restype
-    _lib = L
     return L
 
 
 EXPORTS = ["fq_version", "fq_device_count", "fq_last_error", "fq_set_device_base", "fq_set_select_mode", "fq_get_select_mode", "fq_trim", "fq_last_kernel_ms", "fq_fp2_mul",
-           "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_fp_op", "fq_decode", "fq_decode_spec", "fq_encode", "fq_point_on_curve",
+           "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_fp2_invsqrt", "fq_fp_select", "fq_fp2_select", "fq_fp_op", "fq_decode", "fq_decode_spec", "fq_encode", "fq_point_on_curve",
            "fq_dh", "fq_dh_affine", "fq_dh_base", "fq_mul_base", "fq_dh_endo", "fq_dh_endo_affine", "fq_dh_endo_base",
            "fq_mul_endo_base", "fq_dh_base_comb", "fq_mul_base_comb", "fq_x25519", "fq_host_alloc", "fq_host_free",
-           "fq_dev_alloc", "fq_dev_free", "fq_dev_upload", "fq_dev_download", "fq_dev_run", "fq_dev_last_phase_ms", "fq_dev_flush_l2", "fq_imad_peak"]
+           "fq_dev_alloc", "fq_dev_free", "fq_dev_upload", "fq_dev_download", "fq_dev_run", "fq_dev_run3", "fq_dev_last_phase_ms", "fq_dev_flush_l2", "fq_imad_peak"]
 
 
 def check(rc):

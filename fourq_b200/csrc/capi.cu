@@ -1,32 +1,53 @@
 // capi.cu -- the C ABI of include/fourq_b200.h and the host engine behind it.
 //
-// Host engine.  A call splits its rows into contiguous per-GPU slices (every row is independent, there
-// is no exchange step, hence no collective).  Each GPU runs its slice as a software pipeline of chunks over three
-// CUDA streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.  Chunks of all devices are
-// enqueued round-robin before anything is waited on.  Device staging buffers are kept per (device, stream) and
-// grow on demand; nothing else is cached between calls.  There is no CPU implementation of any operation here.
+// Host engine.  A call splits its rows into contiguous per-GPU slices (every row is independent, there is no
+// exchange step, hence no collective).  Every GPU has its own pair of host threads and its own lock, so slices of one
+// call run concurrently and callers on disjoint GPUs do not wait for each other:
+//
+//   feeder   (one per GPU)  takes the slice, cuts it into chunks (ramped schedule, see chunk_schedule) and for each chunk
+//                           waits for a free stream slot, copies pageable inputs into the slot's pinned staging buffers,
+//                           and enqueues H2D copies, the kernels and the D2H copies on the slot's stream;
+//   drainer  (one per GPU)  waits for each chunk's completion event in order, copies results that were staged for a
+//                           pageable destination into the caller's memory, collects the kernel time and frees the slot.
+//
+// Three stream slots per GPU keep the H2D of chunk c+1, the kernels of chunk c and the D2H (and host copy-out) of chunk c-1
+// in flight together.  Page-locked caller buffers (fq_host_alloc) are used directly in both directions.  Slot buffers,
+// events and streams are created once per GPU and grow on demand; fq_trim wipes and frees them.  There is no CPU
+// implementation of any operation here.
+//
+// tests/hostsim compiles this file with -DFQ_MOCK_CUDA against a small in-process imitation of the CUDA runtime (streams
+// are threads) to exercise exactly this host logic -- chunking, staging, threading, error paths -- without a GPU; that
+// build is test infrastructure and is never shipped or loaded by the product.
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <vector>
+#ifdef FQ_MOCK_CUDA
+#include "mock_cuda_runtime.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include "../../include/fourq_b200.h"
 #include "kernels.h"
 
 namespace {
 
-constexpr int kStreams = 3;
+constexpr int kSlots = 3;
 constexpr int kMaxDev = 16;
-constexpr size_t kFlushBytes = 256u << 20;      // > 126 MB L2
+constexpr int kOperands = 5;                      // a, b, c (inputs), out, status
+constexpr size_t kFlushBytes = 256u << 20;        // > 126 MB L2
 
 thread_local char tl_err[512] = "";
 thread_local float tl_kernel_ms = 0.f;
 thread_local float tl_phase_ms[3] = {0.f, 0.f, 0.f};
-std::mutex g_mu;
-int g_dev_base = 0;
-int g_strict = -1;            // table selection: 0 = masked loads (default), 1 = strict scan, -1 = not yet read from FQ_STRICT_SELECT
+std::atomic<int> g_dev_base{0};
+std::atomic<int> g_strict{-1};    // table selection: 1 = strict scan (default), 0 = masked loads, -1 = not yet read from FQ_STRICT_SELECT
 
 int fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(tl_err, sizeof(tl_err), fmt, ap); va_end(ap);
@@ -36,52 +57,54 @@ int fail(int code, const char* fmt, ...) {
   do { cudaError_t e_ = (call);                                                                        \
        if (e_ != cudaSuccess) return fail(FQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-// device staging buffers of one stream slot (a, b, out, status) and, for pageable result buffers, pinned host staging (2, 3)
-struct Slot {
-  void* buf[4] = {nullptr, nullptr, nullptr, nullptr}; size_t cap[4] = {0, 0, 0, 0};
-  void* hbuf[4] = {nullptr, nullptr, nullptr, nullptr}; size_t hcap[4] = {0, 0, 0, 0};
-  // a chunk whose results still sit in hbuf[2] / hbuf[3] and have to be copied to the caller's (pageable) buffers
-  bool pending = false; size_t p_r0 = 0, p_rows = 0;
-};
-struct DevCtx {
-  bool ready = false;
-  cudaStream_t st[kStreams];
-  Slot slot[kStreams];
-  void* flush = nullptr;
-  void* comb = nullptr;       // per-digit fixed-base tables (kernels_comb.cu)
-  void* dh_scratch[kStreams] = {nullptr, nullptr, nullptr};     // table / plan / projective result handed between the DH (and comb) kernels
-  size_t dh_scratch_cap[kStreams] = {0, 0, 0};
-  int sms = 0;
-};
-DevCtx g_ctx[kMaxDev];
+// ---------------------------------------------------------------- operations
 
-int device_count() {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(FQ_ERR_NO_DEVICE, "no CUDA device available (%s); fourq_b200 has no CPU path", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)); }
-  return n > kMaxDev ? kMaxDev : n;
+// bytes per row of each operand of an operation; chunk_rows = rows of a full pipeline chunk
+struct OpDesc { int op; int in_bytes[3]; int out_bytes; bool status; size_t chunk_rows; };
+
+// rows per full pipeline chunk of the variable-base DH ops: a whole number of waves of k_dh_ladder (2 CTAs x 128 rows per SM)
+// and of k_dh_prep (3 per SM) keeps the tail of each chunk short; FQ_DH_CHUNK_ROWS overrides it (tuning knob, read once,
+// rounded down to a multiple of 128).
+size_t dh_chunk_rows() {
+  static const size_t v = [] {
+    const char* e = getenv("FQ_DH_CHUNK_ROWS");
+    const long long x = e ? atoll(e) : 0;
+    return x >= 128 ? (size_t)x / 128 * 128 : (size_t)148 * 2 * 128 * 12;      // 454,656 rows = 12 waves of k_dh_ladder, 8 of k_dh_prep
+  }();
+  return v;
+}
+// FQ_PIPELINE_RAMP=0 disables the ramped chunk schedule (all chunks full size)
+bool ramp_enabled() {
+  static const bool v = [] { const char* e = getenv("FQ_PIPELINE_RAMP"); return !(e && e[0] == '0'); }();
+  return v;
 }
 
-int ctx_init(int dev) {
-  DevCtx& c = g_ctx[dev];
-  CU(cudaSetDevice(dev));
-  if (c.ready) return FQ_OK;
-  for (int i = 0; i < kStreams; i++) CU(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
-  CU(fqk_device_init(c.st[0]));
-  CU(fqk_comb_init(&c.comb, c.st[0]));
-  CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
-  c.ready = true;
-  return FQ_OK;
+OpDesc describe(int op) {
+  const size_t M = (size_t)1 << 20;
+  switch (op) {
+    case FQ_DEVOP_FP2_MUL: case FQ_DEVOP_FP2_ADD: case FQ_DEVOP_FP2_SUB: return {op, {32, 32, 0}, 32, false, M};
+    case FQ_DEVOP_FP2_SQR: case FQ_DEVOP_FP2_NEG: case FQ_DEVOP_FP2_CONJ: return {op, {32, 0, 0}, 32, false, M};
+    case FQ_DEVOP_FP2_INV: case FQ_DEVOP_FP2_INVSQRT: return {op, {32, 0, 0}, 32, false, M / 4};
+    case FQ_DEVOP_FP2_SELECT: return {op, {32, 32, 1}, 32, false, M};
+    case FQ_DEVOP_FP_SELECT: return {op, {16, 16, 1}, 16, false, M};
+    case FQ_DEVOP_FP_BASE + FQ_FP_MUL: case FQ_DEVOP_FP_BASE + FQ_FP_ADD: case FQ_DEVOP_FP_BASE + FQ_FP_SUB: return {op, {16, 16, 0}, 16, false, M};
+    case FQ_DEVOP_FP_BASE + FQ_FP_SQR: case FQ_DEVOP_FP_BASE + FQ_FP_NEG: return {op, {16, 0, 0}, 16, false, M};
+    case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT: return {op, {16, 0, 0}, 16, false, M / 4};
+    case FQ_DEVOP_DECODE: case FQ_DEVOP_DECODE_SPEC: return {op, {32, 0, 0}, 64, true, M / 4};
+    case FQ_DEVOP_ENCODE: return {op, {64, 0, 0}, 32, false, M};
+    case FQ_DEVOP_ON_CURVE: return {op, {64, 0, 0}, 1, false, M};
+    case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, {32, 32, 0}, 32, true, dh_chunk_rows()};
+    case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, {32, 64, 0}, 64, true, dh_chunk_rows()};
+    case FQ_DEVOP_DH_BASE: case FQ_DEVOP_DH_ENDO_BASE: return {op, {32, 0, 0}, 32, true, M / 8};
+    case FQ_DEVOP_MUL_BASE: case FQ_DEVOP_MUL_ENDO_BASE: return {op, {32, 0, 0}, 32, false, M / 8};
+    // k_comb keeps 2 CTAs of 256 rows resident per SM, each walking over tiles: 148 x 2 x 256 x 4 rows = 4 full tiles per CTA
+    case FQ_DEVOP_DH_BASE_COMB: return {op, {32, 0, 0}, 32, true, (size_t)148 * 2 * 256 * 4};
+    case FQ_DEVOP_MUL_BASE_COMB: return {op, {32, 0, 0}, 32, false, (size_t)148 * 2 * 256 * 4};
+    case FQ_DEVOP_X25519: return {op, {32, 32, 0}, 32, false, M / 8};
+    default: return {-1, {0, 0, 0}, 0, false, 0};
+  }
 }
-
-int slot_reserve(Slot& s, int which, size_t bytes) {
-  if (bytes <= s.cap[which]) return FQ_OK;
-  if (s.buf[which]) CU(cudaFree(s.buf[which]));
-  s.buf[which] = nullptr; s.cap[which] = 0;
-  CU(cudaMalloc(&s.buf[which], bytes));
-  s.cap[which] = bytes;
-  return FQ_OK;
-}
+int operand_bytes(const OpDesc& d, int w) { return w < 3 ? d.in_bytes[w] : w == 3 ? d.out_bytes : (d.status ? 1 : 0); }
 
 bool is_dh_op(int op) { return op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE || op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE; }
 // fixed-base ops: their kernels hand (X, Y, Z) to k_dh_finish through a small scratch
@@ -90,87 +113,168 @@ bool is_comb_op(int op) {
          op == FQ_DEVOP_DH_ENDO_BASE || op == FQ_DEVOP_MUL_ENDO_BASE;
 }
 bool needs_scratch(int op) { return is_dh_op(op) || is_comb_op(op) || op == FQ_DEVOP_X25519; }
+size_t scratch_bytes(int op, size_t rows) {
+  return is_comb_op(op) ? fqk_comb_scratch_bytes(rows) : op == FQ_DEVOP_X25519 ? fqk_x25519_scratch_bytes(rows) : fqk_dh_scratch_bytes(rows);
+}
 
 int strict_mode() {
-  if (g_strict < 0) { const char* e = getenv("FQ_STRICT_SELECT"); g_strict = (e && e[0] == '1') ? 1 : 0; }
-  return g_strict;
-}
-
-int hslot_reserve(Slot& s, int which, size_t bytes) {
-  if (bytes <= s.hcap[which]) return FQ_OK;
-  if (s.hbuf[which]) CU(cudaFreeHost(s.hbuf[which]));
-  s.hbuf[which] = nullptr; s.hcap[which] = 0;
-  CU(cudaHostAlloc(&s.hbuf[which], bytes, cudaHostAllocPortable));
-  s.hcap[which] = bytes;
-  return FQ_OK;
-}
-// true if p is page-locked host memory (cudaHostAlloc / cudaHostRegister): asynchronous copies can use it directly
-bool is_pinned(const void* p) {
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return at.type == cudaMemoryTypeHost;
-}
-
-// grows the kernel scratch of stream slot `si` to what `op` needs for `rows` rows
-int dh_scratch_reserve(DevCtx& c, int si, int op, size_t rows) {
-  size_t bytes = is_comb_op(op) ? fqk_comb_scratch_bytes(rows) : op == FQ_DEVOP_X25519 ? fqk_x25519_scratch_bytes(rows) : fqk_dh_scratch_bytes(rows);
-  if (bytes <= c.dh_scratch_cap[si]) return FQ_OK;
-  if (c.dh_scratch[si]) CU(cudaFree(c.dh_scratch[si]));
-  c.dh_scratch[si] = nullptr; c.dh_scratch_cap[si] = 0;
-  CU(cudaMalloc(&c.dh_scratch[si], bytes));
-  c.dh_scratch_cap[si] = bytes;
-  return FQ_OK;
-}
-// bytes per row of each operand of an operation
-struct OpDesc { int op; int a_bytes, b_bytes, out_bytes; bool status; size_t chunk_rows; };
-
-// rows per full pipeline chunk of the variable-base DH ops: a whole number of waves of k_dh_ladder (2 CTAs x 128 rows per SM)
-// and of k_dh_prep (3 per SM) keeps the tail of each chunk short; FQ_DH_CHUNK_ROWS overrides it (tuning knob, read once).
-size_t dh_chunk_rows() {
-  static size_t v = 0;
-  if (v == 0) {
-    const char* e = getenv("FQ_DH_CHUNK_ROWS");
-    long long x = e ? atoll(e) : 0;
-    v = x >= 128 ? (size_t)x : (size_t)148 * 2 * 128 * 12;      // 454,656 rows = 12 waves of k_dh_ladder, 8 of k_dh_prep
+  int v = g_strict.load();
+  if (v < 0) {                                     // first use: the environment decides unless fq_set_select_mode got there first
+    const char* e = getenv("FQ_STRICT_SELECT");
+    int want = (e && e[0] == '0') ? 0 : 1, expected = -1;
+    v = g_strict.compare_exchange_strong(expected, want) ? want : expected;
   }
   return v;
 }
 
-// FQ_PIPELINE_RAMP=0 disables the ramped chunk schedule of run_host (all chunks full size)
-bool ramp_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FQ_PIPELINE_RAMP"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
-
-OpDesc describe(int op) {
-  switch (op) {
-    case FQ_DEVOP_FP2_MUL: case FQ_DEVOP_FP2_ADD: case FQ_DEVOP_FP2_SUB: return {op, 32, 32, 32, false, (size_t)1 << 20};
-    case FQ_DEVOP_FP2_SQR: case FQ_DEVOP_FP2_NEG: case FQ_DEVOP_FP2_CONJ: return {op, 32, 0, 32, false, (size_t)1 << 20};
-    case FQ_DEVOP_FP2_INV: return {op, 32, 0, 32, false, (size_t)1 << 18};
-    case FQ_DEVOP_FP_BASE + FQ_FP_MUL: case FQ_DEVOP_FP_BASE + FQ_FP_ADD: case FQ_DEVOP_FP_BASE + FQ_FP_SUB: return {op, 16, 16, 16, false, (size_t)1 << 20};
-    case FQ_DEVOP_FP_BASE + FQ_FP_SQR: case FQ_DEVOP_FP_BASE + FQ_FP_NEG: return {op, 16, 0, 16, false, (size_t)1 << 20};
-    case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT: return {op, 16, 0, 16, false, (size_t)1 << 18};
-    case FQ_DEVOP_DECODE: case FQ_DEVOP_DECODE_SPEC: return {op, 32, 0, 64, true, (size_t)1 << 18};
-    case FQ_DEVOP_ENCODE: return {op, 64, 0, 32, false, (size_t)1 << 20};
-    case FQ_DEVOP_ON_CURVE: return {op, 64, 0, 1, false, (size_t)1 << 20};
-    case FQ_DEVOP_DH: case FQ_DEVOP_DH_ENDO: return {op, 32, 32, 32, true, dh_chunk_rows()};
-    case FQ_DEVOP_DH_AFFINE: case FQ_DEVOP_DH_ENDO_AFFINE: return {op, 32, 64, 64, true, dh_chunk_rows()};
-    case FQ_DEVOP_DH_BASE: case FQ_DEVOP_DH_ENDO_BASE: return {op, 32, 0, 32, true, (size_t)1 << 17};
-    case FQ_DEVOP_MUL_BASE: case FQ_DEVOP_MUL_ENDO_BASE: return {op, 32, 0, 32, false, (size_t)1 << 17};
-    // k_comb keeps 2 CTAs of 256 rows resident per SM, each walking over tiles: 148 x 2 x 256 x 4 rows = 4 full tiles per CTA
-    case FQ_DEVOP_DH_BASE_COMB: return {op, 32, 0, 32, true, (size_t)148 * 2 * 256 * 4};
-    case FQ_DEVOP_MUL_BASE_COMB: return {op, 32, 0, 32, false, (size_t)148 * 2 * 256 * 4};
-    case FQ_DEVOP_X25519: return {op, 32, 32, 32, false, (size_t)1 << 17};
-    default: return {-1, 0, 0, 0, false, 0};
+// Chunk schedule of one slice (the same for every device): ramp up from a small chunk (doubling) so that the first kernels
+// start after a short copy, full chunks in the middle, ramp down by halves so that little work and a short copy-back remain
+// exposed at the end.  Slices of at most two small chunks are not split.  No chunk exceeds `full` rows (the staging buffers
+// are sized for exactly that).  bounds[c] .. bounds[c+1] are the rows of chunk c.
+std::vector<size_t> chunk_schedule(size_t rows, size_t full) {
+  std::vector<size_t> bounds;
+  size_t small = full / 8 >= 16384 ? full / 8 : 16384;
+  if (small > full) small = full;
+  const bool ramp = ramp_enabled() && rows > 2 * small;
+  size_t pos = 0, sz = ramp ? small : full;
+  bounds.push_back(0);
+  while (pos < rows) {
+    const size_t left = rows - pos;
+    size_t take = sz < left ? sz : left;
+    if (ramp && left > small && left <= 2 * take) {              // ramp down by halves, in units of 128 rows
+      take = (left / 2 + 127) / 128 * 128;
+      if (take > full) take = full;
+      if (take > left) take = left;
+    }
+    pos += take; bounds.push_back(pos);
+    if (sz < full) sz = sz * 2 < full ? sz * 2 : full;
   }
+  return bounds;
 }
 
-// si: stream slot whose DH scratch is used (reserved by the caller); ev: optional per-kernel events of the DH pipeline
-cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void* out, void* status, size_t n, cudaStream_t s, int si = 0, cudaEvent_t* ev = nullptr) {
+// ---------------------------------------------------------------- per-GPU state
+
+struct SliceJob;
+
+// one stream slot: device staging of every operand, pinned host staging for pageable operands, kernel scratch, events
+struct Slot {
+  cudaStream_t st = nullptr;
+  void* dbuf[kOperands] = {nullptr, nullptr, nullptr, nullptr, nullptr}; size_t dcap[kOperands] = {0, 0, 0, 0, 0};
+  void* hbuf[kOperands] = {nullptr, nullptr, nullptr, nullptr, nullptr}; size_t hcap[kOperands] = {0, 0, 0, 0, 0};
+  void* scratch = nullptr; size_t scratch_cap = 0;      // table / plan / projective result handed between the kernels of an op
+  cudaEvent_t e0 = nullptr, e1 = nullptr, done = nullptr;
+  bool busy = false;                                    // guarded by DevCtx::smu
+};
+struct Chunk { int si; size_t r0, rows; SliceJob* job; };
+
+struct DevCtx {
+  int dev = 0;
+  std::mutex mu;                  // one user of the device context at a time: a slice job or an fq_dev_* call
+  bool ready = false;
+  Slot slot[kSlots];
+  void* flush = nullptr;
+  void* comb = nullptr;           // per-digit fixed-base tables (kernels_comb.cu)
+  int sms = 0;
+  // feeder: slice jobs in submission order
+  std::mutex qmu; std::condition_variable qcv; std::deque<SliceJob*> jobs; bool threads = false;
+  // feeder -> drainer: chunks in enqueue order; also guards Slot::busy and SliceJob::outstanding
+  std::mutex smu; std::condition_variable scv; std::deque<Chunk> chunks;
+};
+DevCtx* g_ctx = nullptr;          // kMaxDev contexts, allocated once and never destroyed (their threads are detached)
+std::once_flag g_ctx_once;
+DevCtx& ctx_of(int dev) {
+  std::call_once(g_ctx_once, [] { g_ctx = new DevCtx[kMaxDev]; for (int i = 0; i < kMaxDev; i++) g_ctx[i].dev = i; });
+  return g_ctx[dev];
+}
+
+int device_count() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(FQ_ERR_NO_DEVICE, "no CUDA device available (%s); fourq_b200 has no CPU path", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)); }
+  return n > kMaxDev ? kMaxDev : n;
+}
+
+// caller holds c.mu
+int ctx_init(DevCtx& c) {
+  CU(cudaSetDevice(c.dev));
+  if (c.ready) return FQ_OK;
+  int rc = FQ_OK;
+  auto undo = [&] {
+    for (int i = 0; i < kSlots; i++) {
+      Slot& s = c.slot[i];
+      if (s.e0) cudaEventDestroy(s.e0);
+      if (s.e1) cudaEventDestroy(s.e1);
+      if (s.done) cudaEventDestroy(s.done);
+      if (s.st) cudaStreamDestroy(s.st);
+      s.e0 = s.e1 = s.done = nullptr; s.st = nullptr;
+    }
+    if (c.comb) { cudaFree(c.comb); c.comb = nullptr; }
+  };
+#define CUI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(FQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); undo(); return rc; } } while (0)
+  for (int i = 0; i < kSlots; i++) {
+    Slot& s = c.slot[i];
+    CUI(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    CUI(cudaEventCreate(&s.e0)); CUI(cudaEventCreate(&s.e1));
+    CUI(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  CUI(fqk_device_init(c.slot[0].st));
+  CUI(fqk_comb_init(&c.comb, c.slot[0].st));
+  CUI(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, c.dev));
+#undef CUI
+  c.ready = true;
+  return FQ_OK;
+}
+
+int dbuf_reserve(Slot& s, int w, size_t bytes) {
+  if (bytes <= s.dcap[w]) return FQ_OK;
+  if (s.dbuf[w]) CU(cudaFree(s.dbuf[w]));
+  s.dbuf[w] = nullptr; s.dcap[w] = 0;
+  CU(cudaMalloc(&s.dbuf[w], bytes));
+  s.dcap[w] = bytes;
+  return FQ_OK;
+}
+int hbuf_reserve(Slot& s, int w, size_t bytes) {
+  if (bytes <= s.hcap[w]) return FQ_OK;
+  if (s.hbuf[w]) CU(cudaFreeHost(s.hbuf[w]));
+  s.hbuf[w] = nullptr; s.hcap[w] = 0;
+  CU(cudaHostAlloc(&s.hbuf[w], bytes, cudaHostAllocPortable));
+  s.hcap[w] = bytes;
+  return FQ_OK;
+}
+int scratch_reserve(Slot& s, int op, size_t rows) {
+  const size_t bytes = scratch_bytes(op, rows);
+  if (bytes <= s.scratch_cap) return FQ_OK;
+  if (s.scratch) CU(cudaFree(s.scratch));
+  s.scratch = nullptr; s.scratch_cap = 0;
+  CU(cudaMalloc(&s.scratch, bytes));
+  s.scratch_cap = bytes;
+  return FQ_OK;
+}
+
+// what kind of memory a caller's host buffer is: page-locked (asynchronous copies use it directly), pageable (staged through
+// the slot's pinned buffers), or not host memory at all (rejected by the host entry points)
+enum PtrKind { PK_PAGEABLE = 0, PK_PINNED = 1, PK_DEVICE = 2 };
+PtrKind classify_one(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return PK_PAGEABLE; }
+  if (at.type == cudaMemoryTypeHost) return PK_PINNED;
+  if (at.type == cudaMemoryTypeDevice) return PK_DEVICE;
+  return PK_PAGEABLE;                                  // unregistered or managed: reachable by memcpy, staged
+}
+PtrKind classify(const void* p, size_t bytes) {
+  if (!p || bytes == 0) return PK_PINNED;
+  const PtrKind first = classify_one(p), last = classify_one((const char*)p + bytes - 1);
+  if (first == PK_DEVICE || last == PK_DEVICE) return PK_DEVICE;
+  return (first == PK_PINNED && last == PK_PINNED) ? PK_PINNED : PK_PAGEABLE;      // partly registered ranges are staged
+}
+
+// ---------------------------------------------------------------- kernels of one chunk
+
+cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, const void* c, void* out, void* status, size_t n, cudaStream_t s, void* scratch, cudaEvent_t* ev = nullptr) {
+  const int strict = strict_mode();
   switch (op) {
-    case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, strict_mode(), cx.comb, a, out, status, n, cx.dh_scratch[si], cx.sms, s);
-    case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, strict_mode(), cx.comb, a, out, nullptr, n, cx.dh_scratch[si], cx.sms, s);
+    case FQ_DEVOP_DH_BASE_COMB: return fqk_comb(1, strict, cx.comb, a, out, status, n, scratch, cx.sms, s);
+    case FQ_DEVOP_MUL_BASE_COMB: return fqk_comb(0, strict, cx.comb, a, out, nullptr, n, scratch, cx.sms, s);
     case FQ_DEVOP_FP2_MUL: return fqk_fp2_op(FQK_MUL, a, b, out, n, s);
     case FQ_DEVOP_FP2_SQR: return fqk_fp2_op(FQK_SQR, a, b, out, n, s);
     case FQ_DEVOP_FP2_INV: return fqk_fp2_op(FQK_INV, a, b, out, n, s);
@@ -178,6 +282,9 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_FP2_SUB: return fqk_fp2_op(FQK_SUB, a, b, out, n, s);
     case FQ_DEVOP_FP2_NEG: return fqk_fp2_op(FQK_NEG, a, b, out, n, s);
     case FQ_DEVOP_FP2_CONJ: return fqk_fp2_op(FQK_CONJ, a, b, out, n, s);
+    case FQ_DEVOP_FP2_INVSQRT: return fqk_fp2_op(FQK_INVSQRT, a, b, out, n, s);
+    case FQ_DEVOP_FP2_SELECT: return fqk_select(2, c, a, b, out, n, s);
+    case FQ_DEVOP_FP_SELECT: return fqk_select(1, c, a, b, out, n, s);
     case FQ_DEVOP_FP_BASE + FQ_FP_MUL: case FQ_DEVOP_FP_BASE + FQ_FP_SQR: case FQ_DEVOP_FP_BASE + FQ_FP_INV: case FQ_DEVOP_FP_BASE + FQ_FP_ADD:
     case FQ_DEVOP_FP_BASE + FQ_FP_SUB: case FQ_DEVOP_FP_BASE + FQ_FP_NEG: case FQ_DEVOP_FP_BASE + FQ_FP_INVSQRT:
       return fqk_fp_op(op - FQ_DEVOP_FP_BASE, a, b, out, n, s);
@@ -185,138 +292,212 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, void*
     case FQ_DEVOP_DECODE_SPEC: return fqk_decode(1, a, out, status, n, s);
     case FQ_DEVOP_ENCODE: return fqk_encode(a, out, n, s);
     case FQ_DEVOP_ON_CURVE: return fqk_on_curve(a, out, n, s);
-    case FQ_DEVOP_DH: return fqk_dh(0, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, strict_mode(), a, out, status, n, cx.dh_scratch[si], s);
-    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, strict_mode(), a, out, nullptr, n, cx.dh_scratch[si], s);
-    case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, strict_mode(), a, b, out, status, n, cx.dh_scratch[si], s, ev);
-    case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, strict_mode(), a, out, status, n, cx.dh_scratch[si], s);
-    case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, strict_mode(), a, out, nullptr, n, cx.dh_scratch[si], s);
-    case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, cx.dh_scratch[si], s);
+    case FQ_DEVOP_DH: return fqk_dh(0, 0, strict, a, b, out, status, n, scratch, s, ev);
+    case FQ_DEVOP_DH_AFFINE: return fqk_dh(1, 0, strict, a, b, out, status, n, scratch, s, ev);
+    case FQ_DEVOP_DH_BASE: return fqk_fixed_base(1, 0, strict, a, out, status, n, scratch, s);
+    case FQ_DEVOP_MUL_BASE: return fqk_fixed_base(0, 0, strict, a, out, nullptr, n, scratch, s);
+    case FQ_DEVOP_DH_ENDO: return fqk_dh(0, 1, strict, a, b, out, status, n, scratch, s, ev);
+    case FQ_DEVOP_DH_ENDO_AFFINE: return fqk_dh(1, 1, strict, a, b, out, status, n, scratch, s, ev);
+    case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, strict, a, out, status, n, scratch, s);
+    case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, strict, a, out, nullptr, n, scratch, s);
+    case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, scratch, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
-struct ChunkEv { int dev; cudaEvent_t e0, e1; };
+// ---------------------------------------------------------------- slices and the per-GPU threads
 
-int run_host(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint8_t* status, size_t n, int ndev) {
-  std::lock_guard<std::mutex> lock(g_mu);
+struct CallState { std::mutex mu; std::condition_variable cv; int remaining = 0; };
+
+struct SliceJob {
+  OpDesc d;
+  const uint8_t* in[3] = {nullptr, nullptr, nullptr};      // whole-call buffers; the slice is rows [lo, hi)
+  uint8_t* out = nullptr; uint8_t* status = nullptr;
+  size_t lo = 0, hi = 0;
+  bool pinned[kOperands] = {true, true, true, true, true};
+  CallState* call = nullptr;
+  // results
+  int rc = FQ_OK; char err[512] = "";
+  float kernel_ms = 0.f;          // sum of the chunks' kernel times (drainer, under smu)
+  size_t outstanding = 0;         // chunks handed to the drainer and not yet retired (under smu)
+};
+
+void job_fail(DevCtx& c, SliceJob* j, int rc) {       // first error of a job wins; tl_err holds the text of this thread's failure
+  std::lock_guard<std::mutex> l(c.smu);
+  if (j->rc == FQ_OK) { j->rc = rc; snprintf(j->err, sizeof(j->err), "%s", tl_err); }
+}
+
+// feeder side of one slice; caller holds c.mu and the device is current
+int feed_slice(DevCtx& c, SliceJob* j) {
+  const OpDesc& d = j->d;
+  const std::vector<size_t> bounds = chunk_schedule(j->hi - j->lo, d.chunk_rows);
+  int rc = FQ_OK;
+  for (size_t ci = 0; ci + 1 < bounds.size() && rc == FQ_OK; ci++) {
+    const size_t r0 = j->lo + bounds[ci], rows = bounds[ci + 1] - bounds[ci];
+    const int si = (int)(ci % kSlots);
+    Slot& s = c.slot[si];
+    { std::unique_lock<std::mutex> l(c.smu); c.scv.wait(l, [&] { return !s.busy; }); if (j->rc != FQ_OK) break; }     // a retired chunk failed: stop feeding
+    if (rows > d.chunk_rows) { rc = fail(FQ_ERR_ARG, "internal: chunk of %zu rows exceeds the staging size %zu", rows, d.chunk_rows); break; }
+    auto body = [&]() -> int {
+      int e;
+      for (int w = 0; w < kOperands; w++) {
+        const int wb = operand_bytes(d, w);
+        if (!wb) continue;
+        if ((e = dbuf_reserve(s, w, d.chunk_rows * wb)) != FQ_OK) return e;
+        if (!j->pinned[w] && (e = hbuf_reserve(s, w, d.chunk_rows * wb)) != FQ_OK) return e;
+      }
+      if (needs_scratch(d.op) && (e = scratch_reserve(s, d.op, d.chunk_rows)) != FQ_OK) return e;
+      for (int w = 0; w < 3; w++) {
+        const int wb = d.in_bytes[w];
+        if (!wb) continue;
+        const uint8_t* src = j->in[w] + r0 * wb;
+        if (!j->pinned[w]) { memcpy(s.hbuf[w], src, rows * wb); src = (const uint8_t*)s.hbuf[w]; }     // pageable input: stage here, overlapping earlier chunks' kernels
+        CU(cudaMemcpyAsync(s.dbuf[w], src, rows * wb, cudaMemcpyHostToDevice, s.st));
+      }
+      CU(cudaEventRecord(s.e0, s.st));
+      CU(launch(c, d.op, s.dbuf[0], s.dbuf[1], s.dbuf[2], s.dbuf[3], s.dbuf[4], rows, s.st, s.scratch));
+      CU(cudaEventRecord(s.e1, s.st));
+      CU(cudaMemcpyAsync(j->pinned[3] ? (void*)(j->out + r0 * d.out_bytes) : s.hbuf[3], s.dbuf[3], rows * d.out_bytes, cudaMemcpyDeviceToHost, s.st));
+      if (d.status) CU(cudaMemcpyAsync(j->pinned[4] ? (void*)(j->status + r0) : s.hbuf[4], s.dbuf[4], rows, cudaMemcpyDeviceToHost, s.st));
+      CU(cudaEventRecord(s.done, s.st));
+      return FQ_OK;
+    };
+    rc = body();
+    if (rc != FQ_OK) { cudaStreamSynchronize(s.st); break; }      // whatever part of the chunk was enqueued must not outlive its buffers
+    { std::lock_guard<std::mutex> l(c.smu); s.busy = true; j->outstanding++; c.chunks.push_back({si, r0, rows, j}); }
+    c.scv.notify_all();
+  }
+  if (rc != FQ_OK) job_fail(c, j, rc);
+  { std::unique_lock<std::mutex> l(c.smu); c.scv.wait(l, [&] { return j->outstanding == 0; }); }
+  return j->rc;
+}
+
+void drainer_main(DevCtx* cp) {
+  DevCtx& c = *cp;
+  bool current = false;
+  for (;;) {
+    Chunk ch;
+    { std::unique_lock<std::mutex> l(c.smu); c.scv.wait(l, [&] { return !c.chunks.empty(); }); ch = c.chunks.front(); c.chunks.pop_front(); }
+    if (!current) { cudaSetDevice(c.dev); current = true; }
+    Slot& s = c.slot[ch.si];
+    SliceJob* j = ch.job;
+    const OpDesc& d = j->d;
+    cudaError_t e = cudaEventSynchronize(s.done);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.e0, s.e1);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      job_fail(c, j, fail(FQ_ERR_CUDA, "chunk at row %zu on device %d failed: %s", ch.r0, c.dev, cudaGetErrorString(e)));
+    } else {
+      if (!j->pinned[3]) memcpy(j->out + ch.r0 * d.out_bytes, s.hbuf[3], ch.rows * d.out_bytes);       // staged results -> caller's pageable memory
+      if (d.status && !j->pinned[4]) memcpy(j->status + ch.r0, s.hbuf[4], ch.rows);
+    }
+    { std::lock_guard<std::mutex> l(c.smu); if (e == cudaSuccess) j->kernel_ms += ms; s.busy = false; j->outstanding--; }
+    c.scv.notify_all();
+  }
+}
+
+void feeder_main(DevCtx* cp) {
+  DevCtx& c = *cp;
+  for (;;) {
+    SliceJob* j;
+    { std::unique_lock<std::mutex> l(c.qmu); c.qcv.wait(l, [&] { return !c.jobs.empty(); }); j = c.jobs.front(); c.jobs.pop_front(); }
+    {
+      std::lock_guard<std::mutex> dl(c.mu);
+      int rc = ctx_init(c);
+      if (rc != FQ_OK) job_fail(c, j, rc); else feed_slice(c, j);
+    }
+    CallState* cs = j->call;
+    { std::lock_guard<std::mutex> l(cs->mu); cs->remaining--; cs->cv.notify_all(); }     // notified under the lock: once it is released the caller may destroy cs and the job
+  }
+}
+
+void submit(DevCtx& c, SliceJob* j) {
+  std::lock_guard<std::mutex> l(c.qmu);
+  if (!c.threads) {
+    std::thread(feeder_main, &c).detach();
+    std::thread(drainer_main, &c).detach();
+    c.threads = true;
+  }
+  c.jobs.push_back(j);
+  c.qcv.notify_one();
+}
+
+int run_host(int op, const uint8_t* a, const uint8_t* b, const uint8_t* cbuf, uint8_t* out, uint8_t* status, size_t n, int ndev) {
   tl_kernel_ms = 0.f;
-  OpDesc d = describe(op);
+  const OpDesc d = describe(op);
   if (d.op < 0) return fail(FQ_ERR_ARG, "unknown operation %d", op);
   if (n == 0) return FQ_OK;
-  if (!a || !out || (d.b_bytes && !b) || (d.status && !status)) return fail(FQ_ERR_ARG, "null buffer");
-  int count = device_count();
+  const uint8_t* in[3] = {a, b, cbuf};
+  for (int w = 0; w < 3; w++) if (d.in_bytes[w] && !in[w]) return fail(FQ_ERR_ARG, "null input buffer");
+  if (!out || (d.status && !status)) return fail(FQ_ERR_ARG, "null output buffer");
+  const int count = device_count();
   if (count < 0) return count;
-  if (ndev < 1 || g_dev_base + ndev > count) return fail(FQ_ERR_ARG, "ndev=%d with device base %d but %d device(s) visible", ndev, g_dev_base, count);
-
-  size_t per = (n + ndev - 1) / ndev;
-  std::vector<ChunkEv> evs;
-  // Chunk schedule of one slice (the same for every device): ramp up from a small chunk (doubling) so that the first kernels
-  // start after a short copy, full chunks in the middle, ramp down by halves so that little work and a short copy-back remain
-  // exposed at the end.  Batches of at most two small chunks are not split.
-  std::vector<size_t> bounds;                        // chunk c covers [bounds[c], bounds[c+1]) of the slice
-  {
-    const size_t full = d.chunk_rows;
-    size_t small = full / 8 >= 16384 ? full / 8 : 16384;
-    if (small > full) small = full;
-    const bool ramp = ramp_enabled() && per > 2 * small;
-    size_t pos = 0, sz = ramp ? small : full;
-    bounds.push_back(0);
-    while (pos < per) {
-      size_t left = per - pos;
-      size_t take = sz < left ? sz : left;
-      if (ramp && left > small && left <= 2 * take) take = (left / 2 + 127) / 128 * 128;   // ramp down by halves
-      pos += take; bounds.push_back(pos);
-      if (sz < full) sz = sz * 2 < full ? sz * 2 : full;
-    }
+  const int base = g_dev_base.load();
+  if (ndev < 1 || base + ndev > count) return fail(FQ_ERR_ARG, "ndev=%d with device base %d but %d device(s) visible", ndev, base, count);
+  bool pinned[kOperands];
+  const void* ptrs[kOperands] = {a, b, cbuf, out, d.status ? status : nullptr};
+  for (int w = 0; w < kOperands; w++) {
+    const int wb = operand_bytes(d, w);
+    const PtrKind k = wb ? classify(ptrs[w], n * wb) : PK_PINNED;
+    if (k == PK_DEVICE) return fail(FQ_ERR_ARG, "operand %d is device memory: the host entry points take host pointers (use fq_dev_run for device buffers)", w);
+    pinned[w] = k == PK_PINNED;
   }
-  size_t max_chunks = bounds.size() - 1;
-  // Results for pageable host buffers go through pinned staging buffers of the stream slot: the D2H copy is asynchronous, and
-  // the host thread copies a chunk's results to the caller's memory once its stream has finished -- at the latest when the
-  // slot is needed again three chunks later -- so these copies (and the page faults of a freshly allocated output array)
-  // overlap the kernels of the chunks in between.  Left to the driver, D2H into pageable memory is staged synchronously:
-  // 39 M instead of 73 M DH rows/s with plain numpy arrays.  Pageable INPUTS are left to the driver (staging them here measured
-  // no better); page-locked buffers (fq_host_alloc, pinned_empty) are used directly in both directions.
-  const bool pin_o = is_pinned(out), pin_s = !d.status || is_pinned(status);
-  // results of the slot's previous chunk: wait for its stream, then staging -> caller's memory
-  auto drain = [&](DevCtx& cx, int si) -> int {
-    Slot& s = cx.slot[si];
-    if (!s.pending) return FQ_OK;
-    s.pending = false;
-    CU(cudaStreamSynchronize(cx.st[si]));
-    if (!pin_o) memcpy(out + s.p_r0 * d.out_bytes, s.hbuf[2], s.p_rows * d.out_bytes);
-    if (d.status && !pin_s) memcpy(status + s.p_r0, s.hbuf[3], s.p_rows);
-    return FQ_OK;
-  };
-  // one chunk of one device: copies in, kernels, copies out on the chunk's stream.  A failing call returns its error from the
-  // lambda; the caller then stops enqueueing and still waits for and cleans up everything that is already in flight.
-  auto enqueue = [&](size_t c, int i) -> int {
-    size_t lo = (size_t)i * per, hi = lo + per < n ? lo + per : n;
-    size_t r0 = lo + bounds[c];
-    if (lo >= n || r0 >= hi) return FQ_OK;
-    size_t r1 = lo + bounds[c + 1] < hi ? lo + bounds[c + 1] : hi;
-    size_t rows = r1 - r0;
-    int dev = g_dev_base + i, e;
-    if ((e = ctx_init(dev)) != FQ_OK) return e;
-    DevCtx& cx = g_ctx[dev];
-    int si = (int)(c % kStreams);
-    Slot& s = cx.slot[si];
-    cudaStream_t st = cx.st[si];
-    if ((e = drain(cx, si)) != FQ_OK) return e;
-    if ((e = slot_reserve(s, 0, d.chunk_rows * d.a_bytes)) != FQ_OK) return e;
-    if (d.b_bytes && (e = slot_reserve(s, 1, d.chunk_rows * d.b_bytes)) != FQ_OK) return e;
-    if ((e = slot_reserve(s, 2, d.chunk_rows * d.out_bytes)) != FQ_OK) return e;
-    if (d.status && (e = slot_reserve(s, 3, d.chunk_rows)) != FQ_OK) return e;
-    if (needs_scratch(op) && (e = dh_scratch_reserve(cx, si, op, d.chunk_rows)) != FQ_OK) return e;
-    if (!pin_o && (e = hslot_reserve(s, 2, d.chunk_rows * d.out_bytes)) != FQ_OK) return e;
-    if (d.status && !pin_s && (e = hslot_reserve(s, 3, d.chunk_rows)) != FQ_OK) return e;
-    CU(cudaMemcpyAsync(s.buf[0], a + r0 * d.a_bytes, rows * d.a_bytes, cudaMemcpyHostToDevice, st));
-    if (d.b_bytes) CU(cudaMemcpyAsync(s.buf[1], b + r0 * d.b_bytes, rows * d.b_bytes, cudaMemcpyHostToDevice, st));
-    ChunkEv ev; ev.dev = i;
-    CU(cudaEventCreate(&ev.e0));
-    if (cudaEventCreate(&ev.e1) != cudaSuccess) { cudaEventDestroy(ev.e0); return fail(FQ_ERR_CUDA, "cudaEventCreate failed"); }
-    evs.push_back(ev);                               // from here on the events are destroyed by the common cleanup
-    CU(cudaEventRecord(ev.e0, st));
-    CU(launch(cx, op, s.buf[0], s.buf[1], s.buf[2], s.buf[3], rows, st, si));
-    CU(cudaEventRecord(ev.e1, st));
-    CU(cudaMemcpyAsync(pin_o ? (void*)(out + r0 * d.out_bytes) : s.hbuf[2], s.buf[2], rows * d.out_bytes, cudaMemcpyDeviceToHost, st));
-    if (d.status) CU(cudaMemcpyAsync(pin_s ? (void*)(status + r0) : s.hbuf[3], s.buf[3], rows, cudaMemcpyDeviceToHost, st));
-    if (!pin_o || !pin_s) { s.pending = true; s.p_r0 = r0; s.p_rows = rows; }
-    return FQ_OK;
-  };
-  int rc = FQ_OK;
-  for (size_t c = 0; c < max_chunks && rc == FQ_OK; c++)
-    for (int i = 0; i < ndev && rc == FQ_OK; i++) rc = enqueue(c, i);
-  // results still in staging buffers (in enqueue order, so that the oldest chunk of each device is copied out first)
-  for (size_t c = max_chunks >= (size_t)kStreams ? max_chunks - kStreams : 0; c < max_chunks; c++)
-    for (int i = 0; i < ndev; i++) {
-      int dev = g_dev_base + i;
-      if (!g_ctx[dev].ready) continue;
-      cudaSetDevice(dev);
-      int e = drain(g_ctx[dev], (int)(c % kStreams));
-      if (e != FQ_OK && rc == FQ_OK) rc = e;
-    }
-  // wait for every device, then collect kernel times
+  const size_t per = (n + ndev - 1) / ndev;
+  CallState cs;
+  std::vector<SliceJob> jobs((size_t)ndev);
+  int used = 0;
   for (int i = 0; i < ndev; i++) {
-    int dev = g_dev_base + i;
-    if (!g_ctx[dev].ready) continue;
-    cudaSetDevice(dev);
-    for (int s = 0; s < kStreams; s++) {
-      cudaError_t e = cudaStreamSynchronize(g_ctx[dev].st[s]);
-      if (e != cudaSuccess && rc == FQ_OK) rc = fail(FQ_ERR_CUDA, "stream sync on device %d failed: %s", dev, cudaGetErrorString(e));
-    }
+    const size_t lo = (size_t)i * per;
+    if (lo >= n) break;
+    SliceJob& j = jobs[i];
+    j.d = d; j.in[0] = a; j.in[1] = b; j.in[2] = cbuf; j.out = out; j.status = status;
+    j.lo = lo; j.hi = lo + per < n ? lo + per : n;
+    for (int w = 0; w < kOperands; w++) j.pinned[w] = pinned[w];
+    j.call = &cs;
+    used++;
   }
-  float per_dev[kMaxDev] = {0};
-  for (auto& ev : evs) {
-    float ms = 0.f;
-    if (rc == FQ_OK && cudaEventElapsedTime(&ms, ev.e0, ev.e1) == cudaSuccess) per_dev[ev.dev] += ms;
-    cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1);
+  { std::lock_guard<std::mutex> l(cs.mu); cs.remaining = used; }
+  for (int i = 0; i < used; i++) submit(ctx_of(base + i), &jobs[i]);
+  { std::unique_lock<std::mutex> l(cs.mu); cs.cv.wait(l, [&] { return cs.remaining == 0; }); }
+  int rc = FQ_OK;
+  for (int i = 0; i < used; i++) {
+    if (jobs[i].rc != FQ_OK && rc == FQ_OK) { rc = jobs[i].rc; snprintf(tl_err, sizeof(tl_err), "%s", jobs[i].err); }
+    if (jobs[i].kernel_ms > tl_kernel_ms) tl_kernel_ms = jobs[i].kernel_ms;
   }
-  for (int i = 0; i < ndev; i++) if (per_dev[i] > tl_kernel_ms) tl_kernel_ms = per_dev[i];
   return rc;
 }
+
+// zeroes (device and pinned staging hold scalars, tables of secret multiples and shared secrets) and frees a slot's buffers
+int slot_wipe_free(Slot& s) {
+  for (int w = 0; w < kOperands; w++) {
+    if (s.dbuf[w]) { CU(cudaMemsetAsync(s.dbuf[w], 0, s.dcap[w], s.st)); }
+    if (s.hbuf[w]) memset(s.hbuf[w], 0, s.hcap[w]);
+  }
+  if (s.scratch) CU(cudaMemsetAsync(s.scratch, 0, s.scratch_cap, s.st));
+  CU(cudaStreamSynchronize(s.st));
+  for (int w = 0; w < kOperands; w++) {
+    if (s.dbuf[w]) { CU(cudaFree(s.dbuf[w])); s.dbuf[w] = nullptr; s.dcap[w] = 0; }
+    if (s.hbuf[w]) { CU(cudaFreeHost(s.hbuf[w])); s.hbuf[w] = nullptr; s.hcap[w] = 0; }
+  }
+  if (s.scratch) { CU(cudaFree(s.scratch)); s.scratch = nullptr; s.scratch_cap = 0; }
+  return FQ_OK;
+}
+
+// locks the context of GPU `dev` for a device-resident call of the calling thread
+struct DevLock {
+  DevCtx* c = nullptr; int rc = FQ_OK;
+  explicit DevLock(int dev) {
+    const int count = device_count();
+    if (count < 0) { rc = count; return; }
+    if (dev < 0 || dev >= count) { rc = fail(FQ_ERR_ARG, "device %d out of range (%d device(s))", dev, count); return; }
+    c = &ctx_of(dev);
+    c->mu.lock();
+    rc = ctx_init(*c);
+    if (rc != FQ_OK) { c->mu.unlock(); c = nullptr; }
+  }
+  ~DevLock() { if (c) c->mu.unlock(); }
+};
 
 }  // namespace
 
@@ -328,74 +509,65 @@ const char* fq_last_error(void) { return tl_err; }
 float fq_last_kernel_ms(void) { return tl_kernel_ms; }
 
 int fq_set_device_base(int first) {
-  std::lock_guard<std::mutex> lock(g_mu);
   int count = device_count();
   if (count < 0) return count;
   if (first < 0 || first >= count) return fail(FQ_ERR_ARG, "device base %d out of range (%d device(s))", first, count);
-  g_dev_base = first;
+  g_dev_base.store(first);
   return FQ_OK;
 }
 
 int fq_trim(void) {
-  std::lock_guard<std::mutex> lock(g_mu);
   int count = device_count();
   if (count < 0) return count;
   for (int dev = 0; dev < count && dev < kMaxDev; dev++) {
-    DevCtx& c = g_ctx[dev];
+    DevCtx& c = ctx_of(dev);
+    std::lock_guard<std::mutex> l(c.mu);
     if (!c.ready) continue;
     CU(cudaSetDevice(dev));
     CU(cudaDeviceSynchronize());
-    for (int si = 0; si < kStreams; si++) {
-      Slot& s = c.slot[si];
-      for (int w = 0; w < 4; w++) {
-        if (s.buf[w]) { CU(cudaFree(s.buf[w])); s.buf[w] = nullptr; s.cap[w] = 0; }
-        if (s.hbuf[w]) { CU(cudaFreeHost(s.hbuf[w])); s.hbuf[w] = nullptr; s.hcap[w] = 0; }
-      }
-      if (c.dh_scratch[si]) { CU(cudaFree(c.dh_scratch[si])); c.dh_scratch[si] = nullptr; c.dh_scratch_cap[si] = 0; }
-    }
+    for (int si = 0; si < kSlots; si++) { int rc = slot_wipe_free(c.slot[si]); if (rc != FQ_OK) return rc; }
     if (c.flush) { CU(cudaFree(c.flush)); c.flush = nullptr; }
   }
   return FQ_OK;
 }
 
 int fq_set_select_mode(int strict) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  if (strict != 0 && strict != 1) return fail(FQ_ERR_ARG, "select mode must be 0 (masked loads) or 1 (strict scan)");
-  g_strict = strict;
+  if (strict != 0 && strict != 1) return fail(FQ_ERR_ARG, "select mode must be 1 (strict scan, default) or 0 (masked loads)");
+  g_strict.store(strict);
   return FQ_OK;
 }
-int fq_get_select_mode(void) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  return strict_mode();
-}
+int fq_get_select_mode(void) { return strict_mode(); }
 
-int fq_fp2_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_MUL, a, b, out, nullptr, n, ndev); }
-int fq_fp2_sqr(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SQR, a, nullptr, out, nullptr, n, ndev); }
-int fq_fp2_inv(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_INV, a, nullptr, out, nullptr, n, ndev); }
-int fq_fp2_add(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_ADD, a, b, out, nullptr, n, ndev); }
-int fq_fp2_sub(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SUB, a, b, out, nullptr, n, ndev); }
-int fq_fp2_neg(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_NEG, a, nullptr, out, nullptr, n, ndev); }
-int fq_fp2_conj(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_CONJ, a, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_MUL, a, b, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_sqr(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SQR, a, nullptr, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_inv(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_INV, a, nullptr, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_invsqrt(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_INVSQRT, a, nullptr, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_add(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_ADD, a, b, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_sub(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SUB, a, b, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_neg(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_NEG, a, nullptr, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_conj(const uint8_t* a, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_CONJ, a, nullptr, nullptr, out, nullptr, n, ndev); }
+int fq_fp2_select(const uint8_t* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP2_SELECT, x, y, c, out, nullptr, n, ndev); }
+int fq_fp_select(const uint8_t* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_FP_SELECT, x, y, c, out, nullptr, n, ndev); }
 int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) {
   if (op < FQ_FP_MUL || op > FQ_FP_INVSQRT) return fail(FQ_ERR_ARG, "unknown GF(p) operation %d", op);
-  return run_host(FQ_DEVOP_FP_BASE + op, a, b, out, nullptr, n, ndev);
+  return run_host(FQ_DEVOP_FP_BASE + op, a, b, nullptr, out, nullptr, n, ndev);
 }
-int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE, enc, nullptr, xy, status, n, ndev); }
-int fq_point_on_curve(const uint8_t* xy, uint8_t* ok, size_t n, int ndev) { return run_host(FQ_DEVOP_ON_CURVE, xy, nullptr, ok, nullptr, n, ndev); }
-int fq_decode_spec(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE_SPEC, enc, nullptr, xy, status, n, ndev); }
-int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev) { return run_host(FQ_DEVOP_ENCODE, xy, nullptr, enc, nullptr, n, ndev); }
-int fq_dh(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH, k, enc_pt, enc_out, status, n, ndev); }
-int fq_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_AFFINE, k, xy, xy_out, status, n, ndev); }
-int fq_dh_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_BASE, k, nullptr, enc_out, status, n, ndev); }
-int fq_mul_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_BASE, k, nullptr, enc_out, nullptr, n, ndev); }
+int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE, enc, nullptr, nullptr, xy, status, n, ndev); }
+int fq_point_on_curve(const uint8_t* xy, uint8_t* ok, size_t n, int ndev) { return run_host(FQ_DEVOP_ON_CURVE, xy, nullptr, nullptr, ok, nullptr, n, ndev); }
+int fq_decode_spec(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE_SPEC, enc, nullptr, nullptr, xy, status, n, ndev); }
+int fq_encode(const uint8_t* xy, uint8_t* enc, size_t n, int ndev) { return run_host(FQ_DEVOP_ENCODE, xy, nullptr, nullptr, enc, nullptr, n, ndev); }
+int fq_dh(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH, k, enc_pt, nullptr, enc_out, status, n, ndev); }
+int fq_dh_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_AFFINE, k, xy, nullptr, xy_out, status, n, ndev); }
+int fq_dh_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_BASE, k, nullptr, nullptr, enc_out, status, n, ndev); }
+int fq_mul_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_BASE, k, nullptr, nullptr, enc_out, nullptr, n, ndev); }
 
-int fq_dh_endo(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO, k, enc_pt, enc_out, status, n, ndev); }
-int fq_dh_endo_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_AFFINE, k, xy, xy_out, status, n, ndev); }
-int fq_dh_endo_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_BASE, k, nullptr, enc_out, status, n, ndev); }
-int fq_mul_endo_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_ENDO_BASE, k, nullptr, enc_out, nullptr, n, ndev); }
-int fq_dh_base_comb(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_BASE_COMB, k, nullptr, enc_out, status, n, ndev); }
-int fq_mul_base_comb(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_BASE_COMB, k, nullptr, enc_out, nullptr, n, ndev); }
-int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_X25519, k, u, out, nullptr, n, ndev); }
+int fq_dh_endo(const uint8_t* k, const uint8_t* enc_pt, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO, k, enc_pt, nullptr, enc_out, status, n, ndev); }
+int fq_dh_endo_affine(const uint8_t* k, const uint8_t* xy, uint8_t* xy_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_AFFINE, k, xy, nullptr, xy_out, status, n, ndev); }
+int fq_dh_endo_base(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_ENDO_BASE, k, nullptr, nullptr, enc_out, status, n, ndev); }
+int fq_mul_endo_base(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_ENDO_BASE, k, nullptr, nullptr, enc_out, nullptr, n, ndev); }
+int fq_dh_base_comb(const uint8_t* k, uint8_t* enc_out, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DH_BASE_COMB, k, nullptr, nullptr, enc_out, status, n, ndev); }
+int fq_mul_base_comb(const uint8_t* k, uint8_t* enc_out, size_t n, int ndev) { return run_host(FQ_DEVOP_MUL_BASE_COMB, k, nullptr, nullptr, enc_out, nullptr, n, ndev); }
+int fq_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int ndev) { return run_host(FQ_DEVOP_X25519, k, u, nullptr, out, nullptr, n, ndev); }
 
 int fq_host_alloc(void** p, size_t bytes) {
   if (!p) return fail(FQ_ERR_ARG, "null pointer");
@@ -406,60 +578,53 @@ int fq_host_alloc(void** p, size_t bytes) {
 }
 int fq_host_free(void* p) { if (p) CU(cudaFreeHost(p)); return FQ_OK; }
 
-static int dev_enter(int dev) {
-  int count = device_count();
-  if (count < 0) return count;
-  if (dev < 0 || dev >= count) return fail(FQ_ERR_ARG, "device %d out of range (%d device(s))", dev, count);
-  return ctx_init(dev);
-}
 int fq_dev_alloc(int dev, void** p, size_t bytes) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
   if (!p) return fail(FQ_ERR_ARG, "null pointer");
   CU(cudaMalloc(p, bytes ? bytes : 1));
   return FQ_OK;
 }
 int fq_dev_free(int dev, void* p) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
   if (p) CU(cudaFree(p));
   return FQ_OK;
 }
 int fq_dev_upload(int dev, void* dst, const void* src, size_t bytes) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
   CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
   return FQ_OK;
 }
 int fq_dev_download(int dev, void* dst, const void* src, size_t bytes) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
   CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
   return FQ_OK;
 }
-int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* status, size_t n, int iters, float* ms) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
-  if (describe(op).op < 0 || iters < 1) return fail(FQ_ERR_ARG, "bad op/iters");
-  DevCtx& cx = g_ctx[dev];
-  cudaStream_t st = cx.st[0];
+int fq_dev_run3(int op, int dev, const void* a, const void* b, const void* c, void* out, void* status, size_t n, int iters, float* ms) {
+  DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
+  const OpDesc d = describe(op);
+  if (d.op < 0 || iters < 1) return fail(FQ_ERR_ARG, "bad op/iters");
+  if ((op == FQ_DEVOP_FP2_INV) && a == out) return fail(FQ_ERR_ARG, "fp2_inv: out must not alias a (the prefix products are parked in out)");
+  DevCtx& cx = *L.c;
+  Slot& s = cx.slot[0];
   const bool dh = is_dh_op(op);
-  if (needs_scratch(op) && (rc = dh_scratch_reserve(cx, 0, op, n)) != FQ_OK) return rc;
-  cudaEvent_t e0, e1, ph[4];
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  int rc;
+  if (needs_scratch(op) && (rc = scratch_reserve(s, op, n)) != FQ_OK) return rc;
+  cudaEvent_t ph[4];
   for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ph[i]));
-  CU(cudaEventRecord(e0, st));
-  for (int i = 0; i < iters; i++) CU(launch(cx, op, a, b, out, status, n, st, 0, (dh && i == iters - 1) ? ph : nullptr));
-  CU(cudaEventRecord(e1, st));
-  CU(cudaEventSynchronize(e1));
+  CU(cudaEventRecord(s.e0, s.st));
+  for (int i = 0; i < iters; i++) CU(launch(cx, op, a, b, c, out, status, n, s.st, s.scratch, (dh && i == iters - 1) ? ph : nullptr));
+  CU(cudaEventRecord(s.e1, s.st));
+  CU(cudaEventSynchronize(s.e1));
   float t = 0.f;
-  CU(cudaEventElapsedTime(&t, e0, e1));
+  CU(cudaEventElapsedTime(&t, s.e0, s.e1));
   tl_phase_ms[0] = tl_phase_ms[1] = tl_phase_ms[2] = 0.f;
   if (dh && n > 0) for (int i = 0; i < 3; i++) CU(cudaEventElapsedTime(&tl_phase_ms[i], ph[i], ph[i + 1]));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ph[i]);
   if (ms) *ms = t / iters;
   return FQ_OK;
+}
+int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* status, size_t n, int iters, float* ms) {
+  return fq_dev_run3(op, dev, a, b, nullptr, out, status, n, iters, ms);
 }
 int fq_dev_last_phase_ms(float* ms3) {
   if (!ms3) return fail(FQ_ERR_ARG, "null pointer");
@@ -467,45 +632,49 @@ int fq_dev_last_phase_ms(float* ms3) {
   return FQ_OK;
 }
 int fq_dev_flush_l2(int dev) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
-  DevCtx& c = g_ctx[dev];
+  DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
+  DevCtx& c = *L.c;
   if (!c.flush) CU(cudaMalloc(&c.flush, kFlushBytes));
-  CU(cudaMemsetAsync(c.flush, 0, kFlushBytes, c.st[0]));
-  CU(cudaStreamSynchronize(c.st[0]));
+  CU(cudaMemsetAsync(c.flush, 0, kFlushBytes, c.slot[0].st));
+  CU(cudaStreamSynchronize(c.slot[0].st));
   return FQ_OK;
 }
 
 int fq_imad_peak(int dev, double* wide_per_s, double* imad32_per_s) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  int rc = dev_enter(dev); if (rc != FQ_OK) return rc;
+  DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
+  Slot& s = L.c->slot[0];
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, dev));
   int blocks = prop.multiProcessorCount * 4, trips = 8192;
   void* scratch = nullptr;
   CU(cudaMalloc(&scratch, (size_t)blocks * 256 * 4));
-  cudaStream_t st = g_ctx[dev].st[0];
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   double res[2] = {0, 0};
   for (int v = 0; v < 2; v++) {
-    CU(fqk_imad_peak(v, scratch, blocks, trips / 8, st));     // warm-up
+    CU(fqk_imad_peak(v, scratch, blocks, trips / 8, s.st));     // warm-up
     float best = 1e30f;
     for (int r = 0; r < 3; r++) {
-      CU(cudaEventRecord(e0, st));
-      CU(fqk_imad_peak(v, scratch, blocks, trips, st));
-      CU(cudaEventRecord(e1, st));
-      CU(cudaEventSynchronize(e1));
-      float t; CU(cudaEventElapsedTime(&t, e0, e1));
+      CU(cudaEventRecord(s.e0, s.st));
+      CU(fqk_imad_peak(v, scratch, blocks, trips, s.st));
+      CU(cudaEventRecord(s.e1, s.st));
+      CU(cudaEventSynchronize(s.e1));
+      float t; CU(cudaEventElapsedTime(&t, s.e0, s.e1));
       if (t < best) best = t;
     }
     res[v] = (double)blocks * 256.0 * trips * 128.0 / (best * 1e-3);
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   CU(cudaFree(scratch));
   if (wide_per_s) *wide_per_s = res[0];
   if (imad32_per_s) *imad32_per_s = res[1];
   return FQ_OK;
 }
+
+#ifdef FQ_MOCK_CUDA
+// test hook (tests/hostsim builds only): the chunk schedule of a slice of `rows` rows with full chunks of `full` rows
+FQ_API size_t fq_test_chunk_schedule(size_t rows, size_t full, size_t* bounds, size_t cap) {
+  const std::vector<size_t> b = chunk_schedule(rows, full);
+  for (size_t i = 0; i < b.size() && i < cap; i++) bounds[i] = b[i];
+  return b.size();
+}
+#endif
 
 }  // extern "C"

@@ -35,6 +35,31 @@ template <int OP> __global__ void __launch_bounds__(256) k_fp_op(const uint4* __
   out[row] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
 }
 
+__global__ void __launch_bounds__(256) k_fp2_invsqrt(const void* a, void* out, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wa[8], wo[8];
+  ld8(a, row, wa);
+  row_fp2_invsqrt(wa, wo);
+  st8(out, row, wo);
+}
+
+// GFp.select / GFp2.select: one 128-bit load per operand half, one condition byte per row
+template <int HALVES> __global__ void __launch_bounds__(256) k_select(const unsigned char* __restrict__ c, const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* __restrict__ out, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wx[4 * HALVES], wy[4 * HALVES], wo[4 * HALVES];
+#pragma unroll
+  for (int h = 0; h < HALVES; h++) {
+    uint4 vx = x[HALVES * row + h], vy = y[HALVES * row + h];
+    wx[4 * h] = vx.x; wx[4 * h + 1] = vx.y; wx[4 * h + 2] = vx.z; wx[4 * h + 3] = vx.w;
+    wy[4 * h] = vy.x; wy[4 * h + 1] = vy.y; wy[4 * h + 2] = vy.z; wy[4 * h + 3] = vy.w;
+  }
+  row_select<HALVES>(c[row], wx, wy, wo);
+#pragma unroll
+  for (int h = 0; h < HALVES; h++) out[HALVES * row + h] = make_uint4(wo[4 * h], wo[4 * h + 1], wo[4 * h + 2], wo[4 * h + 3]);
+}
+
 template <bool SPEC> __global__ void __launch_bounds__(256) k_decode(const void* enc, void* xy, unsigned char* status, size_t n) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
@@ -139,6 +164,7 @@ cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n
     case FQK_SUB: k_fp2_op<FQ_OP_SUB><<<g, 256, 0, s>>>(a, b, out, n); break;
     case FQK_NEG: k_fp2_op<FQ_OP_NEG><<<g, 256, 0, s>>>(a, b, out, n); break;
     case FQK_CONJ: k_fp2_op<FQ_OP_CONJ><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQK_INVSQRT: k_fp2_invsqrt<<<g, 256, 0, s>>>(a, out, n); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -157,6 +183,12 @@ cudaError_t fqk_fp_op(int op, const void* a, const void* b, void* out, size_t n,
     case FQ_FPOP_INVSQRT: k_fp_op<FQ_FPOP_INVSQRT><<<g, 256, 0, s>>>(A, B, O, n); break;
     default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+cudaError_t fqk_select(int halves, const void* c, const void* x, const void* y, void* out, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  if (halves == 2) k_select<2><<<grid_for(n, 256), 256, 0, s>>>((const unsigned char*)c, (const uint4*)x, (const uint4*)y, (uint4*)out, n);
+  else k_select<1><<<grid_for(n, 256), 256, 0, s>>>((const unsigned char*)c, (const uint4*)x, (const uint4*)y, (uint4*)out, n);
   return cudaGetLastError();
 }
 cudaError_t fqk_decode(int spec, const void* enc, void* xy, void* status, size_t n, cudaStream_t s) {

@@ -1,13 +1,19 @@
 // kernels.h -- launch wrappers of kernels.cu (device pointers, one stream).  Internal to the library.
 #pragma once
 #include <cstddef>
+#ifdef FQ_MOCK_CUDA
+#include "mock_cuda_runtime.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
-enum { FQK_MUL = 0, FQK_SQR = 1, FQK_INV = 2, FQK_ADD = 3, FQK_SUB = 4, FQK_NEG = 5, FQK_CONJ = 6 };
+enum { FQK_MUL = 0, FQK_SQR = 1, FQK_INV = 2, FQK_ADD = 3, FQK_SUB = 4, FQK_NEG = 5, FQK_CONJ = 6, FQK_INVSQRT = 7 };
 
 cudaError_t fqk_device_init(cudaStream_t s);   // once per device: fixed-base tables -> __constant__, smem opt-in
 cudaError_t fqk_fp2_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_fp_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);   // GF(p), 16-byte rows, op = FQ_FP_* of the header
+// GFp.select / GFp2.select (fields.py:59-64, :236-238): halves = 1 (16-byte rows) or 2 (32-byte rows), c = one condition byte per row
+cudaError_t fqk_select(int halves, const void* c, const void* x, const void* y, void* out, size_t n, cudaStream_t s);
 cudaError_t fqk_decode(int spec, const void* enc, void* xy, void* status, size_t n, cudaStream_t s);   // spec: draft's t == 0 branch instead of the reference's exception
 cudaError_t fqk_encode(const void* xy, void* enc, size_t n, cudaStream_t s);
 cudaError_t fqk_on_curve(const void* xy, void* ok, size_t n, cudaStream_t s);

@@ -63,7 +63,10 @@ k_dh_prep(const void* __restrict__ k, const void* __restrict__ pt, DhScratch sc,
   sc.meta[row] = D.plan.first | (st << 8);
 }
 
-template <bool ENDO, bool STRICT> __global__ void __launch_bounds__(FQ_DH_THREADS, 2)
+#ifndef FQ_LADDER_MAXREG
+#define FQ_LADDER_MAXREG 255
+#endif
+template <bool ENDO, bool STRICT> __global__ void __maxnreg__(FQ_LADDER_MAXREG)
 k_dh_ladder(DhScratch sc) {
   extern __shared__ uint4 smem[];
   const size_t row = (size_t)blockIdx.x * FQ_DH_THREADS + threadIdx.x;

@@ -52,6 +52,44 @@ template <int OP> FQ_FN void row_fp_op(const u32* a, const u32* b, u32* out) {
   for (int i = 0; i < 4; i++) out[i] = r.v[i];
 }
 
+// fields.py:201-230 GFp2.invsqrt, with the reference's control flow: the raw test a[1] == 0 (:204) picks the GF(p) branch, every
+// other row the norm branch; the reference's two comparisons `== -1` (:217, :223) can never be true (GFp.mul returns values in
+// [0, p)), so neither the 'not square' exception nor the second delta is ever taken.  8 words in, 8 canonical words out.
+FQ_FN void row_fp2_invsqrt(const u32* a, u32* out) {
+  const bool a1_raw_zero = (a[4] | a[5] | a[6] | a[7]) == 0;
+  const fp a0 = fp_from_u128(fp_set(a[0], a[1], a[2], a[3])), a1 = fp_from_u128(fp_set(a[4], a[5], a[6], a[7]));
+  fp x0, x1;
+  if (a1_raw_zero) {
+    fp t = fp_canon(fp_invsqrt_c(a0));                                          // :205
+    const bool is_one = fp_eq_canon(fp_canon(fp_mul(a0, fp_sqr(t))), fp_one());   // :206
+    x0 = is_one ? t : fp_zero(); x1 = is_one ? fp_zero() : t;                    // :207-209
+  } else {
+    fp n = fp_add(fp_sqr(a0), fp_sqr(a1));                                      // :214
+    fp sv = fp_invsqrt_c(n);                                                    // :215
+    fpb S = fp_prep(sv);
+    fp c = fp_mul_prep(n, S);                                                   // :216
+    fp delta = fp_half(fp_add(a0, c));                                          // :220
+    fp g = fp_invsqrt_c(delta);                                                 // :221
+    fp h = fp_mul(delta, g);                                                    // :222
+    x0 = fp_mul_prep(h, S);                                                     // :228
+    x1 = fp_neg(fp_half(fp_mul(fp_mul_prep(a1, S), g)));                        // :229
+  }
+  x0 = fp_canon(x0); x1 = fp_canon(x1);
+  FQ_UNROLL
+  for (int i = 0; i < 4; i++) { out[i] = x0.v[i]; out[4 + i] = x1.v[i]; }
+}
+
+// fields.py:59-64 GFp.select / :236-238 GFp2.select on raw words: out = y ^ ((mask * c) & (x ^ y)) with mask = 2^512 - 1, i.e.
+// mask * c = -c modulo 2^128.  W words per row half (4), HALVES halves per row that share the condition byte c.
+template <int HALVES> FQ_FN void row_select(u32 c, const u32* x, const u32* y, u32* out) {
+  const u32 m0 = 0u - c, mh = c ? 0xffffffffu : 0u;           // limbs of -c mod 2^128: the borrow fills the upper limbs
+  FQ_UNROLL
+  for (int h = 0; h < HALVES; h++) {
+    FQ_UNROLL
+    for (int i = 0; i < 4; i++) { const u32 m = i == 0 ? m0 : mh; out[4 * h + i] = y[4 * h + i] ^ (m & (x[4 * h + i] ^ y[4 * h + i])); }
+  }
+}
+
 // decode: 8 words -> 16 words (x0|x1|y0|y1), zero-filled on failure
 template <bool SPEC = false> FQ_FN u32 row_decode(const u32* enc, u32* xy) {
   fp2 x, y;

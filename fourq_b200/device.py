@@ -19,10 +19,11 @@ def set_device(first):
 
 
 def set_select_mode(strict):
-    """Table selection of every scalar multiplication: False = masked loads (default: predicated loads, no select
-    instructions; the shared-memory activity of a load depends on how the digits are spread over a warp), True = strict scan
-    (every lane loads every entry and selects in registers; DH 1-2 % slower, comb keygen 8 % slower).  Same outputs.
-    FQ_STRICT_SELECT=1 selects the strict scan at start-up."""
+    """Table selection of every scalar multiplication: True = strict scan (default: every lane loads every table entry and
+    selects in registers, no digit-dependent memory activity of any kind), False = masked loads (opt-in for non-secret
+    scalars: predicated loads, no select instructions, DH 1-2 % and comb keygen 8 % faster, but the shared-memory activity of
+    a load depends on how the digits are spread over a warp).  Same outputs.  FQ_STRICT_SELECT=0 selects masked loads at
+    start-up."""
     _lib.check(_lib.lib().fq_set_select_mode(1 if strict else 0))
 
 
@@ -100,11 +101,12 @@ class DeviceBuffer:
             pass
 
 
-def dev_run(op, dev, a, b, out, status, n, iters=1):
-    """Launches the kernel of `op` (a key of _lib.DEVOP) on device buffers; returns average milliseconds per launch."""
+def dev_run(op, dev, a, b, out, status, n, iters=1, c=None):
+    """Launches the kernel of `op` (a key of _lib.DEVOP) on device buffers; returns average milliseconds per launch.
+    c: third input operand (the condition bytes of fp_select / fp2_select)."""
     ms = ctypes.c_float()
     g = lambda x: x.ptr if x is not None else None  # noqa: E731
-    _lib.check(_lib.lib().fq_dev_run(_lib.DEVOP[op], int(dev), g(a), g(b), g(out), g(status), int(n), int(iters), ctypes.byref(ms)))
+    _lib.check(_lib.lib().fq_dev_run3(_lib.DEVOP[op], int(dev), g(a), g(b), g(c), g(out), g(status), int(n), int(iters), ctypes.byref(ms)))
     return float(ms.value)
 
 

@@ -26,6 +26,18 @@ def _binary(fn_name, a, b, ndev):
     return out
 
 
+def _select(fn_name, width, c, x, y, ndev):
+    """out = y ^ ((mask * c) & (x ^ y)) on the device (fields.py:59-64): c == 1 -> x, c == 0 -> y, no reduction."""
+    x = _lib.rows(x, width, "x")
+    y = _lib.rows(y, width, "y")
+    c = np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.uint8)
+    if x.shape != y.shape or c.shape[0] != x.shape[0]:
+        raise ValueError("c must have one entry per row and x, y the same shape")
+    out = np.empty_like(x)
+    _lib.check(getattr(_lib.lib(), fn_name)(_lib.ptr(c), _lib.ptr(x), _lib.ptr(y), _lib.ptr(out), x.shape[0], ndev))
+    return out
+
+
 class GFp2:
     """Static methods named after fields.py GFp2.*"""
 
@@ -58,9 +70,12 @@ class GFp2:
         return _unary("fq_fp2_conj", a, ndev)
 
     @staticmethod
-    def select(c, x, y):         # fields.py:237-238; c is a (N,) 0/1 array.  Pure data movement, done by numpy.
-        c = np.asarray(c).astype(bool).reshape(-1, 1)
-        return np.where(c, _lib.rows(x, 32, "x"), _lib.rows(y, 32, "y"))
+    def invsqrt(a, ndev=1):      # fields.py:201-230 (the reference's own control flow, see include/fourq_b200.h)
+        return _unary("fq_fp2_invsqrt", a, ndev)
+
+    @staticmethod
+    def select(c, x, y, ndev=1):     # fields.py:236-238; c is a (N,) array of 0/1 (uint8), one condition per row
+        return _select("fq_fp2_select", 32, c, x, y, ndev)
 
 
 def _fp(op, a, b, ndev):
@@ -107,9 +122,8 @@ class GFp:
         return _fp("invsqrt", x, None, ndev)
 
     @staticmethod
-    def select(c, x, y):         # fields.py:60-64; c is a (N,) 0/1 array.  Pure data movement, done by numpy.
-        c = np.asarray(c).astype(bool).reshape(-1, 1)
-        return np.where(c, _lib.rows(x, 16, "x"), _lib.rows(y, 16, "y"))
+    def select(c, x, y, ndev=1):     # fields.py:59-64; c is a (N,) array of 0/1 (uint8), one condition per row
+        return _select("fq_fp_select", 16, c, x, y, ndev)
 
 
 def pack(pairs):

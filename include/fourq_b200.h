@@ -15,7 +15,9 @@
  *     device every call returns FQ_ERR_NO_DEVICE.
  *   - return value: 0 (FQ_OK) or a negative FQ_ERR_*; fq_last_error() gives the text (thread-local).
  *   - per-row outcome in status[n] (uint8): see FQ_ST_*.  Rows that fail are zero-filled in the output.
- *   - thread-safe: calls are serialised by an internal mutex; per-device contexts are created lazily.
+ *   - thread-safe: every GPU has its own lock and its own pair of host threads (one feeds chunks to the GPU, one retires
+ *     them), so the slices of a call run concurrently and callers on disjoint GPUs do not wait for each other; calls that
+ *     share a GPU are served in submission order.  Per-device contexts are created lazily.
  */
 #ifndef FOURQ_B200_H
 #define FOURQ_B200_H
@@ -27,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FQ_VERSION 107
+#define FQ_VERSION 200
 
 #if defined(__GNUC__)
 #define FQ_API __attribute__((visibility("default")))
@@ -58,14 +60,15 @@ FQ_API float fq_last_kernel_ms(void);
 
 /* Constant-time table selection of every scalar multiplication (csrc/dh.cuh).  In both modes every thread issues the loads
  * of ALL table entries from digit-independent addresses and there is no secret-dependent branch.
- *   0 (default)  masked loads: the digit sets each load's predicate and a lane whose predicate is off transfers nothing; no
- *                select instructions at all.  The number of shared-memory wavefronts of a load then depends on how the
- *                digits are distributed over the 32 lanes of a warp: 0.4 % of the ladder time between the extremes "all rows
- *                of every warp use the same scalar" and "all differ" (profiles/r01_ct_timing.jsonl).
- *   1            strict scan: every lane loads every entry and keeps one with a predicated select per word, so not even the
- *                memory activity of a load depends on a digit (no measurable timing difference); variable-base DH 1-2 %
- *                slower, fixed-base comb keygen 8 % slower.
- * Same outputs.  The environment variable FQ_STRICT_SELECT=1 selects 1 at start-up. */
+ *   1 (default)  strict scan: every lane loads every entry and keeps one with a predicated select per word, so not even the
+ *                memory activity of a load depends on a digit: kernel time is flat across scalar distributions
+ *                (profiles/r01_ct_timing.jsonl, r02_ct_timing.jsonl).  This is what draft-ladd-cfrg-4q.md:653-656, :753-755 ask for.
+ *   0 (opt-in)   masked loads: the digit sets each load's predicate and a lane whose predicate is off transfers nothing; no
+ *                select instructions at all, 1-2 % faster for variable-base DH and 8 % for the comb keygen.  The number of
+ *                shared-memory wavefronts of a load then depends on how the digits are distributed over the 32 lanes of a warp:
+ *                0.4 % of the ladder time between the extremes "all rows of every warp use the same scalar" and "all differ".
+ *                Only for non-secret scalars (verification-style workloads, benchmarks).
+ * Same outputs.  The environment variable FQ_STRICT_SELECT=0 selects 0 at start-up. */
 FQ_API int fq_set_select_mode(int strict);
 FQ_API int fq_get_select_mode(void);
 
@@ -78,6 +81,17 @@ FQ_API int fq_fp2_add(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n
 FQ_API int fq_fp2_sub(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
 FQ_API int fq_fp2_neg(const uint8_t* a, uint8_t* out, size_t n, int ndev);
 FQ_API int fq_fp2_conj(const uint8_t* a, uint8_t* out, size_t n, int ndev);
+/* fields.py GFp2.invsqrt :201-230 (the reference marks it "not constant-time"; curve4q.py never calls it, fields.py:391 tests it).
+ * Bit-compatible with the reference's control flow, including its two comparisons with -1 that can never be true: a row with
+ * a[1] == 0 (raw value) takes the GF(p) branch :204-209, every other row the norm branch :214-230, whatever the
+ * quadratic character of the input.  a, out are (n,32). */
+FQ_API int fq_fp2_invsqrt(const uint8_t* a, uint8_t* out, size_t n, int ndev);
+/* fields.py GFp.select :59-64 and GFp2.select :236-238:  out = y ^ ((mask * c) & (x ^ y)), i.e. c == 1 -> x, c == 0 -> y, bit for
+ * bit (no reduction: x and y pass through as they are).  c is (n,) uint8, one condition per row; x, y, out are (n,16) for GF(p)
+ * and (n,32) for GF(p^2) (the same c for both halves).  Other values of c behave as in the reference's expression:
+ * the mask is (2^512 - 1) * c, i.e. -c modulo 2^128. */
+FQ_API int fq_fp_select(const uint8_t* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n, int ndev);
+FQ_API int fq_fp2_select(const uint8_t* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n, int ndev);
 
 /* ---- GF(p) field ops on 16-byte rows (little-endian 128-bit values): fields.py GFp.mul :42, sqr :48, inv :67-106,
  * add :30, sub :36, neg :54, invsqrt :110-122.  a, b, out are (n,16); b is ignored by the unary ops (may be NULL).  Inputs may
@@ -149,6 +163,9 @@ FQ_API int fq_host_free(void* p);
 #define FQ_DEVOP_FP2_SUB 4
 #define FQ_DEVOP_FP2_NEG 5
 #define FQ_DEVOP_FP2_CONJ 6
+#define FQ_DEVOP_FP2_INVSQRT 7
+#define FQ_DEVOP_FP2_SELECT 8  /* a = x, b = y, c = cond (1 byte per row), out: fq_dev_run3 */
+#define FQ_DEVOP_FP_SELECT 9   /* the same on 16-byte rows */
 #define FQ_DEVOP_FP_BASE 32    /* FQ_DEVOP_FP_BASE + FQ_FP_*: GF(p) ops on 16-byte rows, a (, b), out */
 #define FQ_DEVOP_DECODE 16     /* a = enc, out = xy, status */
 #define FQ_DEVOP_ENCODE 17     /* a = xy, out = enc */
@@ -170,6 +187,8 @@ FQ_API int fq_dev_free(int dev, void* p);
 FQ_API int fq_dev_upload(int dev, void* dst, const void* src, size_t bytes);
 FQ_API int fq_dev_download(int dev, void* dst, const void* src, size_t bytes);
 FQ_API int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* status, size_t n, int iters, float* ms);
+/* the same with a third input operand (FQ_DEVOP_FP_SELECT / FQ_DEVOP_FP2_SELECT: c = the condition bytes) */
+FQ_API int fq_dev_run3(int op, int dev, const void* a, const void* b, const void* c, void* out, void* status, size_t n, int iters, float* ms);
 /* CUDA-event milliseconds of the three kernels (prepare, ladder, finish) of the last launch of the last fq_dev_run of
  * this thread with a variable-base DH op (FQ_DEVOP_DH, _DH_AFFINE, _DH_ENDO, _DH_ENDO_AFFINE); zeros otherwise. */
 FQ_API int fq_dev_last_phase_ms(float* ms3);

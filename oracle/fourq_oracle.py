@@ -143,6 +143,26 @@ def f2_inv(a):               # fields.py:194-199   conj(a) / (a0^2 + a1^2); inv(
     return f2_mul((n, 0), f2_conj(a))
 
 
+def f2_invsqrt(a):           # fields.py:201-230   the reference's control flow; its two `== -1` tests can never hold
+    """a is taken as given (the raw a[1] == 0 test of :204 sees unreduced values); every field op reduces."""
+    if a[1] == 0:                                             # :204-209
+        t = fp_invsqrt(a[0])
+        return (t, 0) if fp_mul(a[0], fp_sqr(t)) == 1 else (0, t)
+    n = fp_add(fp_sqr(a[0]), fp_sqr(a[1]))                    # :214
+    s = fp_invsqrt(n)                                         # :215
+    c = fp_mul(n, s)                                          # :216  (the 'not square' exception of :217-218 is unreachable)
+    half = 1 << 126                                           # GFp.half
+    delta = fp_mul(fp_add(a[0], c), half)                     # :220
+    g = fp_invsqrt(delta)                                     # :221
+    h = fp_mul(delta, g)                                      # :222  (the second delta of :223-226 is unreachable)
+    return (fp_mul(h, s), fp_neg(fp_mul(fp_mul(fp_mul(a[1], s), g), half)) % P127)       # :228-230
+
+
+def select_raw(c, x, y, bits=128):
+    """fields.py:59-64  y ^ ((mask * c) & (x ^ y)) with mask = 2^512 - 1, on `bits`-bit values: c = 1 -> x, c = 0 -> y, no reduction."""
+    return y ^ ((((1 << 512) - 1) * c) & (x ^ y)) & ((1 << bits) - 1)
+
+
 # ------------------------------------------------------------------ Curve4Q constants (curve4q.py:8-20)
 
 D = (0xe40000000000000142, 0x5e472f846657e0fcb3821488f1fc0c8d)
@@ -614,7 +634,18 @@ def row_fp2(op, a, b=None):
         return f2_to_bytes(f2_neg((A[0] % P127, A[1] % P127)))
     if op == "conj":
         return f2_to_bytes(f2_conj((A[0] % P127, A[1] % P127)))
+    if op == "invsqrt":
+        return f2_to_bytes(f2_invsqrt(A))
     raise ValueError(op)
+
+
+def row_select(c, x, y):
+    """GFp.select / GFp2.select (fields.py:59-64, :236-238) on 16- or 32-byte rows with the condition byte c."""
+    out = b""
+    for h in range(len(x) // 16):
+        xi, yi = int.from_bytes(x[16 * h:16 * h + 16], "little"), int.from_bytes(y[16 * h:16 * h + 16], "little")
+        out += select_raw(c, xi, yi).to_bytes(16, "little")
+    return out
 
 
 def row_fp(op, a, b=None):

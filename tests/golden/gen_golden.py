@@ -285,6 +285,30 @@ def main():
         xv.append([k.hex(), u.hex(), bytes(c25519.x25519(k, u)).hex()])
     dump("x25519.json", {"x25519": xv})
 
+    # ------------------------------------------------------------------ select and GFp2.invsqrt (fields.py:59-64, :236-238, :201-230)
+    # A separate file and RNG stream, so that the vectors above stay byte-identical to the round-1 files.
+    rng = random.Random(0x5E1EC7)
+    sel = {"fp_select": [], "fp2_select": [], "fp2_invsqrt": []}
+    vals = edge + [rng.getrandbits(128) for _ in range(40)]
+    for i, x in enumerate(vals):
+        y = vals[(i * 5 + 2) % len(vals)]
+        for c in (0, 1):                                     # the reference's contract; unreduced values pass through unchanged
+            sel["fp_select"].append([c, le16(x).hex(), le16(y).hex(), le16(GFp.select(c, x, y)).hex()])
+    for c in (2, 3, 128, 255):                               # what the reference's expression gives for other c (mask * c)
+        x, y = rng.getrandbits(128), rng.getrandbits(128)
+        sel["fp_select"].append([c, le16(x).hex(), le16(y).hex(), le16(GFp.select(c, x, y) & ((1 << 128) - 1)).hex()])
+    for i in range(48):
+        a = (rng.getrandbits(128), rng.getrandbits(128)); b = (rng.getrandbits(128), rng.getrandbits(128))
+        for c in (0, 1):
+            sel["fp2_select"].append([c, f2b(a), f2b(b), f2b(GFp2.select(c, a, b))])
+    inv_in = [(a, b) for a in (0, 1, 2, 3, 4, p - 1, p - 2, 1 << 126) for b in (0, 1, p - 1, 5)]
+    inv_in += [(rng.getrandbits(127) % p, 0) for _ in range(16)]                              # the GF(p) branch, squares and non-squares
+    inv_in += [(rng.getrandbits(127) % p, rng.getrandbits(127) % p) for _ in range(96)]
+    inv_in += [(5, p), (p, 7), (p + 3, 0), ((1 << 128) - 1, (1 << 128) - 1)]                 # unreduced: a[1] == 0 is tested on the raw value
+    for a in inv_in:
+        sel["fp2_invsqrt"].append([f2b(a), f2b(GFp2.invsqrt(a))])
+    dump("select.json", sel)
+
 
 if __name__ == "__main__":
     main()

@@ -247,4 +247,28 @@ int sim_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n) {
   }
   return 0;
 }
+// fields.py GFp2.invsqrt :201-230 (rows.cuh row_fp2_invsqrt)
+int sim_fp2_invsqrt(const uint8_t* a, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) { u32 wa[8], wo[8]; memcpy(wa, a + 32 * i, 32); row_fp2_invsqrt(wa, wo); memcpy(out + 32 * i, wo, 32); }
+  return 0;
+}
+// fields.py GFp.select :59-64 (halves = 1, 16-byte rows) / GFp2.select :236-238 (halves = 2, 32-byte rows)
+int sim_select(int halves, const uint8_t* c, const uint8_t* x, const uint8_t* y, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wx[8], wy[8], wo[8];
+    memcpy(wx, x + 16 * halves * i, 16 * halves); memcpy(wy, y + 16 * halves * i, 16 * halves);
+    if (halves == 2) row_select<2>(c[i], wx, wy, wo); else row_select<1>(c[i], wx, wy, wo);
+    memcpy(out + 16 * halves * i, wo, 16 * halves);
+  }
+  return 0;
+}
+// curve4q.py PointOnCurve :23-29 on x | y rows (kernels.cu k_on_curve)
+int sim_on_curve(const uint8_t* xy, uint8_t* ok, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wi[16]; memcpy(wi, xy + 64 * i, 64);
+    fp2 x = fp2_canon(row_load_fp2(wi)), y = fp2_canon(row_load_fp2(wi + 8));
+    ok[i] = pt_on_curve(x, y) ? 1 : 0;
+  }
+  return 0;
+}
 }  // extern "C"

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(libpath):
         assert hasattr(L, s), s
     from fourq_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared_symbols()
-    assert _lib.lib().fq_version() == 107
+    assert _lib.lib().fq_version() == 200
 
 
 def test_no_cpu_fallback(libpath):

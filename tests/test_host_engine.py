@@ -1,0 +1,211 @@
+"""The host engine of fourq_b200/csrc/capi.cu (slices, chunk schedule, pinned staging, the per-GPU feeder / drainer threads,
+error paths) exercised WITHOUT a GPU: tests/hostsim builds capi.cu against a mock CUDA runtime whose streams are threads and
+whose kernels are the CPU simulation of the device code.  Test infrastructure only -- the product library is never built
+this way and has no CPU path."""
+import ctypes
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from fourq_b200 import _lib
+from oracle import c_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIM_DIR = os.path.join(HERE, "hostsim")
+CSRC = os.path.join(HERE, "..", "fourq_b200", "csrc")
+
+
+def _stale(target, extra=()):
+    srcs = [os.path.join(SIM_DIR, f) for f in os.listdir(SIM_DIR) if f.endswith((".cpp", ".h", ".sh"))]
+    srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")) or f == "capi.cu"] + list(extra)
+    return not os.path.exists(target) or os.path.getmtime(target) < max(os.path.getmtime(s) for s in srcs)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    so = os.path.join(SIM_DIR, "libfq_mockengine.so")
+    if _stale(so):
+        subprocess.check_call(["sh", os.path.join(SIM_DIR, "build.sh")])
+    L = _lib.bind(ctypes.CDLL(so))
+    for name in ("mock_violations", "mock_memcpy_bytes"):
+        getattr(L, name).restype = ctypes.c_long
+    L.mock_live_allocs.restype = ctypes.c_long
+    L.mock_live_allocs.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
+    L.mock_fail_nth.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.fq_test_chunk_schedule.restype = ctypes.c_size_t
+    L.fq_test_chunk_schedule.argtypes = [ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t]
+    L.mock_set_device_count(4)
+    yield L
+    L.mock_set_jitter_us(0)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return ctypes.CDLL(os.path.join(SIM_DIR, "libfq_hostsim.so"))
+
+
+def pinned(L, shape):
+    n = int(np.prod(shape))
+    p = ctypes.c_void_p()
+    assert L.fq_host_alloc(ctypes.byref(p), n) == 0
+    arr = np.frombuffer((ctypes.c_uint8 * n).from_address(p.value), np.uint8).reshape(shape)
+    return arr, p
+
+
+P = _lib.ptr
+
+
+def test_chunk_schedule_never_exceeds_the_staging_size(eng):
+    """with a chunk size that is not a multiple of 128 the ramp-down used to round a chunk past the buffers."""
+    buf = (ctypes.c_size_t * 40000)()
+    for full in (128, 1000, 16384, 100000, 131072, 303104, 454656, 500000, 1 << 20):
+        for rows in (1, 127, 128, 129, full - 1, full, full + 1, 2 * full + 5, 3 * full + 77, 10 * full + 1, (1 << 21) + 3, (1 << 22) + 12345):
+            if rows < 1:
+                continue
+            m = eng.fq_test_chunk_schedule(rows, full, buf, 40000)
+            b = [buf[i] for i in range(m)]
+            assert b[0] == 0 and b[-1] == rows and all(0 < y - x <= full for x, y in zip(b, b[1:])), (full, rows, b)
+
+
+@pytest.mark.parametrize("ndev", [1, 2, 3, 4])
+def test_fp2_mul_many_chunks_pageable_and_pinned(eng, sim, ndev):
+    eng.mock_set_jitter_us(200)
+    rng = np.random.default_rng(10 + ndev)
+    n = 700_001 + 4099 * ndev                     # several ramped chunks per slice (full chunk = 2^20 rows, small = 2^17)
+    a = rng.integers(0, 256, (n, 32), np.uint8); b = rng.integers(0, 256, (n, 32), np.uint8)
+    ref = np.empty_like(a)
+    sim.sim_fp2_op(0, P(a), P(b), P(ref), ctypes.c_size_t(n))
+    out = np.zeros_like(a)
+    assert eng.fq_fp2_mul(P(a), P(b), P(out), n, ndev) == 0, eng.fq_last_error()
+    assert (out == ref).all()
+    assert eng.fq_last_kernel_ms() > 0
+    # page-locked buffers are used directly: no staging copies of the results
+    pa, ha = pinned(eng, (n, 32)); pb, hb = pinned(eng, (n, 32)); po, ho = pinned(eng, (n, 32))
+    pa[:] = a; pb[:] = b; po[:] = 0
+    assert eng.fq_fp2_mul(ha, hb, ho, n, ndev) == 0, eng.fq_last_error()
+    assert (po == ref).all()
+    # mixed: pinned inputs, pageable output
+    out[:] = 0
+    assert eng.fq_fp2_mul(ha, hb, P(out), n, ndev) == 0
+    assert (out == ref).all()
+    for h in (ha, hb, ho):
+        assert eng.fq_host_free(h) == 0
+    assert eng.mock_violations() == 0
+
+
+def test_dh_slices_match_single_device_and_the_oracle(eng):
+    eng.mock_set_jitter_us(0)
+    rng = np.random.default_rng(5)
+    n = 1203
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    pub = np.empty_like(k)
+    assert eng.fq_mul_base_comb(P(rng.integers(0, 256, (n, 32), np.uint8)), P(pub), n, 4) == 0
+    pub[7] = 0xFF; pub[600] = 0                      # failing rows travel through the slices too
+    want, wst = c_oracle.dh(k, pub)
+    for fn in (eng.fq_dh_endo, eng.fq_dh):
+        for ndev in (1, 3):
+            out = np.zeros_like(k); st = np.full(n, 9, np.uint8)
+            assert fn(P(k), P(pub), P(out), P(st), n, ndev) == 0, eng.fq_last_error()
+            assert (out == want).all() and (st == wst).all()
+    assert eng.mock_violations() == 0
+
+
+def test_three_input_select_through_the_engine(eng):
+    rng = np.random.default_rng(6)
+    n = 5000
+    x = rng.integers(0, 256, (n, 32), np.uint8); y = rng.integers(0, 256, (n, 32), np.uint8)
+    c = rng.integers(0, 2, n, np.uint8)
+    out = np.empty_like(x)
+    assert eng.fq_fp2_select(P(c), P(x), P(y), P(out), n, 2) == 0
+    assert (out == np.where(c.reshape(-1, 1) == 1, x, y)).all()
+    out16 = np.empty((n, 16), np.uint8)
+    x16, y16 = np.ascontiguousarray(x[:, :16]), np.ascontiguousarray(y[:, :16])
+    assert eng.fq_fp_select(P(c), P(x16), P(y16), P(out16), n, 3) == 0
+    assert (out16 == np.where(c.reshape(-1, 1) == 1, x16, y16)).all()
+
+
+def test_argument_errors(eng):
+    a = np.zeros((4, 32), np.uint8); out = np.zeros_like(a)
+    assert eng.fq_fp2_sqr(P(a), P(out), 4, 0) == _lib.FQ_ERR_ARG
+    assert eng.fq_fp2_sqr(P(a), P(out), 4, 5) == _lib.FQ_ERR_ARG          # 4 mock devices
+    assert eng.fq_fp2_sqr(None, P(out), 4, 1) == _lib.FQ_ERR_ARG
+    assert eng.fq_fp2_sqr(P(a), P(out), 0, 1) == 0
+    d = ctypes.c_void_p()
+    assert eng.fq_dev_alloc(0, ctypes.byref(d), 128) == 0
+    assert eng.fq_fp2_sqr(P(a), d, 4, 1) == _lib.FQ_ERR_ARG               # a device pointer is not a host buffer
+    assert b"device memory" in eng.fq_last_error()
+    assert eng.fq_dev_free(0, d) == 0
+    eng.mock_set_device_count(0)
+    try:
+        assert eng.fq_fp2_sqr(P(a), P(out), 4, 1) == _lib.FQ_ERR_NO_DEVICE
+    finally:
+        eng.mock_set_device_count(4)
+
+
+@pytest.mark.parametrize("api,nth", [(b"cudaMemcpyAsync", 1), (b"cudaMemcpyAsync", 7), (b"cudaMalloc", 1), (b"cudaEventRecord", 5),
+                                     (b"cudaEventSynchronize", 2), (b"cudaHostAlloc", 1)])
+def test_injected_cuda_failures_return_an_error_and_do_not_wedge_the_engine(eng, sim, api, nth):
+    rng = np.random.default_rng(8)
+    n = 600_000
+    a = rng.integers(0, 256, (n, 32), np.uint8); out = np.zeros_like(a)
+    assert eng.fq_trim() == 0                       # buffers gone: the next call has to allocate (and stage: pageable arrays)
+    eng.mock_fail_nth(api, nth)
+    rc = eng.fq_fp2_sqr(P(a), P(out), n, 2)
+    eng.mock_fail_nth(api, 0)
+    assert rc == _lib.FQ_ERR_CUDA and eng.fq_last_error() != b""
+    ref = np.empty_like(a)
+    sim.sim_fp2_op(1, P(a), None, P(ref), ctypes.c_size_t(n))
+    assert eng.fq_fp2_sqr(P(a), P(out), n, 2) == 0, eng.fq_last_error()
+    assert (out == ref).all()
+
+
+def test_concurrent_callers(eng, sim):
+    """Several host threads issue multi-device calls at once: every GPU serves them in submission order, results stay right."""
+    eng.mock_set_jitter_us(100)
+    rng = np.random.default_rng(9)
+    n = 200_000
+    errs = []
+
+    def work(seed, ndev):
+        r = np.random.default_rng(seed)
+        a = r.integers(0, 256, (n, 32), np.uint8); b = r.integers(0, 256, (n, 32), np.uint8)
+        ref = np.empty_like(a); out = np.zeros_like(a)
+        sim.sim_fp2_op(3, P(a), P(b), P(ref), ctypes.c_size_t(n))
+        for _ in range(3):
+            out[:] = 0
+            if eng.fq_fp2_add(P(a), P(b), P(out), n, ndev) != 0 or not (out == ref).all():
+                errs.append((seed, ndev))
+    ts = [threading.Thread(target=work, args=(100 + i, 1 + i % 4)) for i in range(6)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errs and eng.mock_violations() == 0
+    del rng
+
+
+def test_trim_wipes_and_frees_everything(eng):
+    k = np.random.default_rng(3).integers(0, 256, (300, 32), np.uint8); out = np.empty_like(k)
+    assert eng.fq_mul_base_comb(P(k), P(out), 300, 2) == 0
+    nb = ctypes.c_long()
+    assert eng.mock_live_allocs(1, ctypes.byref(nb)) > 0                   # pinned staging exists (pageable arrays)
+    eng.mock_expect_zero_on_free(1)
+    try:
+        assert eng.fq_trim() == 0
+    finally:
+        eng.mock_expect_zero_on_free(0)
+    assert eng.mock_violations() == 0                                      # every freed staging / scratch buffer had been zeroed
+    assert eng.mock_live_allocs(1, ctypes.byref(nb)) == 0
+    assert eng.mock_live_allocs(2, ctypes.byref(nb)) <= 4                  # only the per-device comb tables stay
+
+
+@pytest.mark.parametrize("san", ["tsan", "asan"])
+def test_engine_stress_under_sanitizers(san):
+    """ThreadSanitizer / AddressSanitizer + UBSan over the engine's threads, staging and scratch sizing (engine_stress.cpp)."""
+    exe = os.path.join(SIM_DIR, "engine_stress_" + san)
+    if _stale(exe):
+        subprocess.check_call(["sh", os.path.join(SIM_DIR, "build.sh"), san])
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 second_deadlock_stack=1", ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "Sanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "engine_stress ok" in r.stdout

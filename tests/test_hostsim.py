@@ -326,3 +326,98 @@ def test_x25519_special_values_vs_oracle(sim):
     k = _rows(kk); u = _rows(uu); out = np.zeros(32 * len(kk), np.uint8)
     sim.sim_x25519(_p(k), _p(u), _p(out), ctypes.c_size_t(len(kk)))
     assert [bytes(out[32 * i:32 * i + 32]) for i in range(len(kk))] == [O.x25519(a, b) for a, b in zip(kk, uu)]
+
+
+def test_select_and_fp2_invsqrt_golden(sim, golden):
+    """rows.cuh row_select / row_fp2_invsqrt against vectors produced by the reference's GFp.select, GFp2.select, GFp2.invsqrt."""
+    g = golden["select"]
+    for key, halves in (("fp_select", 1), ("fp2_select", 2)):
+        rows = g[key]
+        c = np.array([r[0] for r in rows], np.uint8)
+        x = _rows([H(r[1]) for r in rows]); y = _rows([H(r[2]) for r in rows]); out = np.zeros_like(x)
+        assert sim.sim_select(halves, _p(c), _p(x), _p(y), _p(out), ctypes.c_size_t(len(rows))) == 0
+        w = 16 * halves
+        assert [bytes(out[w * i:w * i + w]).hex() for i in range(len(rows))] == [r[3] for r in rows]
+    rows = g["fp2_invsqrt"]
+    a = _rows([H(r[0]) for r in rows]); out = np.zeros_like(a)
+    assert sim.sim_fp2_invsqrt(_p(a), _p(out), ctypes.c_size_t(len(rows))) == 0
+    assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[1] for r in rows]
+    # random rows against the oracle, including the GF(p) branch
+    rng = random.Random(21)
+    A = [(rng.getrandbits(128).to_bytes(16, "little") + (b"\0" * 16 if i % 5 == 0 else rng.getrandbits(128).to_bytes(16, "little"))) for i in range(400)]
+    a = _rows(A); out = np.zeros_like(a)
+    sim.sim_fp2_invsqrt(_p(a), _p(out), ctypes.c_size_t(len(A)))
+    assert [bytes(out[32 * i:32 * i + 32]) for i in range(len(A))] == [O.row_fp2("invsqrt", x) for x in A]
+
+
+@pytest.mark.parametrize("rows_per_thread", [1, 4, 16, 32])
+def test_batched_inversion_with_zero_rows_in_every_position(sim, rows_per_thread):
+    """batchinv.cuh (k_fp2_inv_batched): zeros, p (an alias of zero), ones and random values mixed inside the groups that share
+    one inversion, ragged batch sizes; inv(0) = 0 as in fields.py:194-199."""
+    rng = random.Random(31 + rows_per_thread)
+    p = O.P127
+    for n in (1, 2, 63, 64, 65, 1000, 64 * rows_per_thread + 1):
+        A = []
+        for i in range(n):
+            r = rng.random()
+            if r < 0.15:
+                a = (rng.choice([0, p, 1 << 127]) if rng.random() < 0.7 else 0, rng.choice([0, p]))     # zero in every disguise (2^127 = 1: not zero)
+            elif r < 0.25:
+                a = (1, 0)
+            else:
+                a = (rng.getrandbits(128), rng.getrandbits(128))
+            A.append(a[0].to_bytes(16, "little") + a[1].to_bytes(16, "little"))
+        a = _rows(A); out = np.full_like(a, 0xEE)
+        assert sim.sim_fp2_inv_batched(_p(a), _p(out), ctypes.c_size_t(n), rows_per_thread) == 0
+        got = [bytes(out[32 * i:32 * i + 32]) for i in range(n)]
+        assert got == [O.row_fp2("inv", x) for x in A], (n, rows_per_thread)
+
+
+def test_finish_kernel_mixed_groups(sim):
+    """batchinv.cuh FinishIO (k_dh_finish): projective rows with Z = 0 / failed status / the neutral point mixed with good rows in
+    one shared inversion; compared with the per-row R1toAffine + neutral check + encode of the oracle."""
+    rng = random.Random(41)
+    p = O.P127
+    G = (O.GX, O.GY)
+    pts = []
+    P = O.affine_to_r1(*G)
+    for _ in range(40):
+        P = O.dbl(P)
+        pts.append(O.r1_to_affine(P))
+    n = 333
+    rows, st_in, want, wst = [], [], [], []
+    for i in range(n):
+        r = rng.random()
+        x, y = pts[i % len(pts)]
+        lam = (rng.getrandbits(127) % p or 1, rng.getrandbits(127) % p)
+        X, Y, Z = O.f2_mul(x, lam), O.f2_mul(y, lam), lam
+        st = 0
+        if r < 0.1:
+            X, Y, Z, st = (rng.getrandbits(127), 5), (7, rng.getrandbits(127)), (0, 0), 4          # failed validation: garbage with Z = 0
+        elif r < 0.2:
+            st = rng.choice([1, 2, 3, 4])                                                          # failed validation, harmless coordinates
+        elif r < 0.3:
+            X, Y, Z = (0, 0), lam, lam                                                             # the neutral point (0, 1)
+        rows.append(b"".join(v.to_bytes(16, "little") for v in (X[0], X[1], Y[0], Y[1], Z[0], Z[1])))
+        st_in.append(st)
+        if st != 0:
+            want.append(bytes(32)); wst.append(st)
+        elif X == (0, 0) and Y == Z:
+            want.append(bytes(32)); wst.append(5)
+        else:
+            zi = O.f2_inv(Z)
+            want.append(bytes(O.encode(O.f2_mul(X, zi), O.f2_mul(Y, zi)))); wst.append(0)
+    for rpt in (1, 4, 16):
+        a = _rows(rows); s_in = np.array(st_in, np.uint8); out = np.full(32 * n, 0xEE, np.uint8); st = np.full(n, 0xEE, np.uint8)
+        assert sim.sim_finish_rows(_p(a), _p(s_in), _p(out), _p(st), ctypes.c_size_t(n), rpt, 1) == 0
+        assert [bytes(out[32 * i:32 * i + 32]) for i in range(n)] == want and list(st) == wst
+
+
+def test_x25519_shared_inversion(sim, golden):
+    """x25519.cuh X25519FinIO: the RFC / golden rows through the batched finish (one z^(p-2) chain per 16 rows), u = 0 rows (z2 = 0)
+    mixed in."""
+    rows = golden["x25519"]["x25519"]
+    k = _rows([H(r[0]) for r in rows]); u = _rows([H(r[1]) for r in rows]); out = np.zeros_like(k)
+    for rpt in (1, 16):
+        assert sim.sim_x25519_batched(_p(k), _p(u), _p(out), ctypes.c_size_t(len(rows)), rpt) == 0
+        assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[2] for r in rows]

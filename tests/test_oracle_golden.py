@@ -34,6 +34,14 @@ def test_fp_inv_invsqrt(golden):
         assert O.fp_to_le(O.fp_invsqrt(int.from_bytes(H(x), "little"))).hex() == out
 
 
+def test_select_and_fp2_invsqrt(golden):
+    g = golden["select"]
+    for c, x, y, out in g["fp_select"] + g["fp2_select"]:
+        assert O.row_select(c, H(x), H(y)).hex() == out
+    for a, out in g["fp2_invsqrt"]:
+        assert O.row_fp2("invsqrt", H(a)).hex() == out
+
+
 @pytest.mark.parametrize("op", ["add", "sub", "mul", "sqr", "neg", "inv", "invsqrt"])
 def test_fp_rows(golden, op):
     for r in golden["fp"][op]:
