@@ -17,6 +17,12 @@ One JSON line is printed by rank 0:
              step (SURVEY.md 8d "tight" count of decode + DH + encode: 58,284 endo / 103,836 windowed per row)
   cpu_baseline  the oracle (Python restatement of the reference) on the host's cores over a bounded sample; the same
              sample is compared bit-for-bit with the GPU output
+  configs    (rank 0, after the timed regions, bounded): BASELINE cfg 2 (2^26 fp2 mul / sqr against the HBM peak, 2^20 inv), cfg 4
+             (2^24 fixed-base keygen), cfg 5 (2^20 X25519 and its ratio to Curve4Q DH), kernel time with device-resident data
+  e2e_pageable  the e2e call with plain numpy arrays (what a drop-in user passes); the engine stages them through pinned buffers
+  inproc     (N > 1 only) rank 0 alone drives all N GPUs through the C ABI's own slice dispatcher (ndev = N) while the other
+             ranks wait on a CPU barrier: cfg 4 strong scaling (2^24 rows at ndev 1 and N) and cfg 3 (N x 2^20 rows), each
+             compared byte for byte with the ndev = 1 result
 --impl reference times the reference's CPU algorithm (the oracle port: the reference itself is Python 2 and cannot run
 here) with multiprocessing on all host cores, on a bounded sample per step.
 """
@@ -41,6 +47,10 @@ ROWS_PER_GPU = 1 << 20
 IMADS_PER_ROW = {"windowed": 103836, "endo": 58284}
 # ... and the share of the dominant kernel k_dh_ladder (the main loop): 62 x (4 DBL + ADD) / 64 x (DBL + ADD), DBL = 272, ADD = 384
 IMADS_PER_ROW_LADDER = {"windowed": 62 * (4 * 272 + 384), "endo": 64 * (272 + 384)}
+# the finish kernel shares one GF(p^2) inversion (1,504 multiply-adds) between 16 rows at the price of 3 multiplications
+# per row, so the step executes fewer multiply-adds than the reference's one-inversion-per-row count: the cheaper figure is cited
+INV_ROWS = 16
+INV_SAVING = 1504 - (1504 // INV_ROWS + 3 * 48)
 BYTES_PER_ROW = 96              # 32 scalar + 32 point + 32 out
 WORKLOAD = "cfg3 variable-base DH (decode+validate+[392]P+[k]Q+inversion+encode), 2^20 (scalar, encoded point) rows per GPU"
 
@@ -204,6 +214,117 @@ def _quiet_stdout():
     return real
 
 
+def _best_ms(fqdev, op, dev, a, b, out, st, n, reps=3, warm=1):
+    for _ in range(warm):
+        fqdev.dev_run(op, dev, a, b, out, st, n)
+    best = 1e30
+    for _ in range(reps):
+        fqdev.flush_l2(dev)
+        best = min(best, fqdev.dev_run(op, dev, a, b, out, st, n))
+    return best
+
+
+def measure_configs(fq, fqdev, dev, wide_peak, hbm, dh_ms, algorithm, quick=False):
+    """BASELINE configs 2, 4 and 5 on one GPU, kernel time with device-resident inputs (CUDA events, best of 3, L2 flushed),
+    each batch spot-checked against the oracle before it is reported.  About 1 s of GPU time plus the set-up of the arrays."""
+    from oracle import fourq_oracle as O
+    out = {}
+    # ---- cfg 2: 2^26 mul / sqr (HBM-bound: 96 / 64 B per element), 2^20 inv (multiplier-bound)
+    n = 1 << (20 if quick else 26)
+    base = np.random.default_rng(2).integers(0, 256, (1 << 20, 32), np.uint8)
+    a = np.tile(base, (n >> 20, 1)); b = np.tile(base[::-1], (n >> 20, 1))
+    da = fqdev.DeviceBuffer.from_host(dev, a); db = fqdev.DeviceBuffer.from_host(dev, b); do = fqdev.DeviceBuffer(dev, n * 32)
+    c2 = {"rows": n}
+    for op, nbytes in (("fp2_mul", 96), ("fp2_sqr", 64)):
+        ms = _best_ms(fqdev, op, dev, da, db if op == "fp2_mul" else None, do, None, n)
+        got = do.to_host((128, 32))
+        for j in range(128):
+            assert bytes(got[j]) == O.row_fp2(op[4:], bytes(a[j]), bytes(b[j]) if op == "fp2_mul" else None), (op, j)
+        c2[op + "_ms"] = ms; c2[op + "_gbs"] = n * nbytes / ms / 1e6; c2[op + "_frac_hbm"] = n * nbytes / ms / 1e6 / hbm
+    ni = 1 << 20
+    ms = _best_ms(fqdev, "fp2_inv", dev, da, None, do, None, ni)
+    got = do.to_host((64, 32))
+    for j in range(64):
+        assert bytes(got[j]) == O.row_fp2("inv", bytes(a[j])), j
+    inv_imads = 1504 // INV_ROWS + 3 * 48
+    c2.update({"fp2_inv_rows": ni, "fp2_inv_ms": ms, "fp2_inv_per_s": ni / ms * 1e3, "fp2_inv_imads_per_row": inv_imads,
+               "fp2_inv_frac_imad": ni * inv_imads / ms * 1e3 / wide_peak, "hbm_peak_gbs": hbm})
+    out["cfg2"] = c2
+    del da, db, do, a, b
+    # ---- cfg 4: 2^24 fixed-base keygen [k]G on per-digit tables
+    n = 1 << (20 if quick else 24)
+    k = np.random.default_rng(5).integers(0, 256, (n, 32), np.uint8)
+    dk = fqdev.DeviceBuffer.from_host(dev, k); do = fqdev.DeviceBuffer(dev, n * 32)
+    ms = _best_ms(fqdev, "mul_base_comb", dev, dk, None, do, None, n)
+    got = do.to_host((2048, 32))
+    for j in range(0, 2048, 64):
+        assert bytes(got[j]) == O.row_mul_base(bytes(k[j])), j
+    comb_imads = 62 * 336 + 1504 // INV_ROWS + 5 * 48
+    out["cfg4"] = {"rows": n, "kernel_ms": ms, "rows_per_s": n / ms * 1e3, "imads_per_row": comb_imads, "frac_imad": n * comb_imads / ms * 1e3 / wide_peak,
+                   "algorithm": "per-digit tables: 62 mixed additions, no doubling (comb.cuh)"}
+    del dk, do
+    # ---- cfg 5: 2^20 X25519 next to 2^20 Curve4Q DH (the batched compare.py)
+    n = 1 << 20
+    kk = np.random.default_rng(6).integers(0, 256, (n, 32), np.uint8); uu = np.random.default_rng(7).integers(0, 256, (n, 32), np.uint8)
+    dk = fqdev.DeviceBuffer.from_host(dev, kk); du = fqdev.DeviceBuffer.from_host(dev, uu); do = fqdev.DeviceBuffer(dev, n * 32); ds = fqdev.DeviceBuffer(dev, n)
+    ms_x = _best_ms(fqdev, "x25519", dev, dk, du, do, None, n, reps=2)
+    got = do.to_host((32, 32))
+    for j in range(32):
+        assert bytes(got[j]) == O.x25519(bytes(kk[j]), bytes(uu[j])), j
+    pub = fq.MUL_base(np.random.default_rng(4).integers(0, 256, (n, 32), np.uint8))
+    dp = fqdev.DeviceBuffer.from_host(dev, pub)
+    other = "windowed" if algorithm == "endo" else "endo"
+    ms_other = _best_ms(fqdev, "dh" if other == "windowed" else "dh_endo", dev, dk, dp, do, ds, n, reps=2)
+    ms_alg = {algorithm: dh_ms, other: ms_other}
+    out["cfg5"] = {"rows": n, "x25519_ms": ms_x, "x25519_rows_per_s": n / ms_x * 1e3, "dh_endo_ms": ms_alg["endo"], "dh_windowed_ms": ms_alg["windowed"],
+                   "ratio_endo": ms_x / ms_alg["endo"], "ratio_windowed": ms_x / ms_alg["windowed"],
+                   "x25519_frac_imad": n * 123078 / ms_x * 1e3 / wide_peak,
+                   "note": "Curve4Q DH throughput / X25519 throughput; the draft claims >2x with endomorphisms, 1.2-1.6x without (draft-ladd-cfrg-4q.md:170-171)"}
+    return out
+
+
+def measure_inproc(fq, world, algorithm, quick=False):
+    """Rank 0 alone, all `world` GPUs in ONE process through the C ABI's slice dispatcher (capi.cu: one feeder and one drainer
+    thread per GPU): cfg 4 strong scaling (2^24 keygen rows at ndev = 1 and ndev = world) and cfg 3 (world x 2^20 DH rows),
+    page-locked host arrays, wall clock, best of 3; every multi-GPU result is compared byte for byte with the ndev = 1 result."""
+    res = {"n_gpus": world}
+    fq.set_device(0)
+    n4 = 1 << (20 if quick else 24)
+    pk = fq.pinned_empty((n4, 32)); pk[:] = np.random.default_rng(5).integers(0, 256, (n4, 32), np.uint8)
+    po1 = fq.pinned_empty((n4, 32)); poN = fq.pinned_empty((n4, 32))
+
+    def best(fn, reps=3):
+        fn()
+        t = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); t = min(t, time.perf_counter() - t0)
+        return t
+    t1 = best(lambda: fq.MUL_base(pk, out=po1, ndev=1))
+    tN = best(lambda: fq.MUL_base(pk, out=poN, ndev=world))
+    kN = fq.last_kernel_ms()
+    same4 = bool((po1 == poN).all())
+    res["cfg4"] = {"rows": n4, "ndev1_rows_per_s": n4 / t1, "ndevN_rows_per_s": n4 / tN, "ndev1_ms": t1 * 1e3, "ndevN_ms": tN * 1e3, "speedup": t1 / tN,
+                   "ndevN_max_device_kernel_ms": kN, "scaling": "strong", "parity_vs_ndev1": same4}
+    rows = (1 << (18 if quick else 20))
+    n3 = rows * world
+    k3 = fq.pinned_empty((n3, 32)); k3[:] = np.random.default_rng(3).integers(0, 256, (n3, 32), np.uint8)
+    p3 = fq.pinned_empty((n3, 32)); p3[:] = poN[:n3] if n3 <= n4 else np.tile(poN, ((n3 + n4 - 1) // n4, 1))[:n3]
+    o3 = fq.pinned_empty((n3, 32)); s3 = fq.pinned_empty((n3,))
+    tN3 = best(lambda: fq.DH(k3, p3, out=o3, status=s3, ndev=world, algorithm=algorithm))
+    m = min(n3, 1 << 18)                                 # a slice that crosses the first slice boundary when world > 4; ndev = 1 on the same rows
+    lo = max(0, rows - m // 2)
+    o1, s1 = fq.DH(k3[lo:lo + m], p3[lo:lo + m], ndev=1, algorithm=algorithm)
+    same3 = bool((o1 == o3[lo:lo + m]).all() and (s1 == s3[lo:lo + m]).all())
+    res["cfg3"] = {"rows": n3, "rows_per_s": n3 / tN3, "ms": tN3 * 1e3, "scaling": "weak", "parity_vs_ndev1": same3, "parity_rows": int(m)}
+    res["parity_vs_ndev1"] = same4 and same3
+    res["note"] = ("one process drives all GPUs through fq_mul_base_comb / fq_dh_endo with ndev = %d (contiguous slices, per-device feeder and drainer "
+                   "threads, no collective); pinned host arrays, wall clock of the whole call, best of 3" % world)
+    if not res["parity_vs_ndev1"]:
+        raise SystemExit("PARITY FAILURE: the ndev = %d result differs from ndev = 1" % world)
+    return res
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,6 +335,8 @@ def main():
     ap.add_argument("--algorithm", default="endo", choices=["windowed", "endo"],
                     help="scalar-multiplication algorithm of the reference: MUL_windowed or MUL_endo (same outputs)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="rows of the CPU baseline sample (default 256 per core; 0 = skip)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg 2 / 4 / 5 measurements and the in-process multi-GPU phase")
+    ap.add_argument("--quick", action="store_true", help="developer runs: small cfg 2 / 4 / in-process batches")
     ap.add_argument("--verify-rows", type=int, default=-1, help="rows of rank 0's batch compared bit for bit with the C oracle after the timed regions (default all; 0 = skip)")
     args = ap.parse_args()
     out = _quiet_stdout()
@@ -232,6 +355,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")       # CPU-side barrier: ranks that wait on it leave their GPU idle
 
     def barrier():
         if dist is not None:
@@ -291,12 +415,35 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * rows * args.steps / e2e_s
     assert (out_e2e == out_dev).all() and (st_e2e == st_dev).all() and not st_dev.any()
+    # the same call with plain (pageable) numpy arrays, outputs allocated by the call: what a drop-in user of the reference writes
+    for _ in range(2):
+        fq.DH(k, pub, algorithm=args.algorithm)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_pg, st_pg = fq.DH(k, pub, algorithm=args.algorithm)
+    barrier()
+    pg_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_pageable = world * rows * args.steps / pg_s
+    assert (out_pg == out_dev).all() and (st_pg == st_dev).all()
+
+    # ---- in-process multi-GPU phase: rank 0 drives all GPUs, the other ranks wait on the CPU barrier with idle GPUs
+    inproc = None
+    if dist is not None and not args.no_configs:
+        del dk, dp, dout, dst
+        fq.trim()
+        barrier()
+        if rank == 0:
+            inproc = measure_inproc(fq, world, args.algorithm, quick=args.quick)
+            fq.set_device(local_rank)
+        dist.barrier(group=cpu_group)
 
     # ---- roofline denominator measured live + CPU baseline and parity on a sample (rank 0)
     line = None
     if rank == 0:
         wide_peak, imad_peak = fqdev.imad_peak(local_rank)
-        step_achieved = (value / world) * imads                      # all three kernels of a step
+        imads_run = imads - INV_SAVING                               # the step as executed: one inversion per INV_ROWS rows
+        step_achieved = (value / world) * imads_run                  # all three kernels of a step
         ph = [sum(p[i] for p in phase_ms) / len(phase_ms) for i in range(3)]      # rank 0's average ms: prepare, ladder, finish
         ladder_achieved = rows * IMADS_PER_ROW_LADDER[args.algorithm] / (ph[1] * 1e-3)
         peaks = {}
@@ -314,16 +461,19 @@ def main():
             pass
         roofline = {"bound": "imad", "kernel": "k_dh_ladder", "achieved": ladder_achieved / 1e12, "peak": wide_peak / 1e12, "unit": "T IMAD.WIDE/s",
                     "frac": ladder_achieved / wide_peak, "traffic": traffic,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_dh_ladder launch from the committed ncu --set full capture (profiles/traffic.json), not re-measured in this run",
+                    "frac_of_imad32_peak": ladder_achieved / imad_peak,
                     "kernel_ms": {"k_dh_prep": ph[0], "k_dh_ladder": ph[1], "k_dh_finish": ph[2]},
-                    "step": {"achieved": step_achieved / 1e12, "frac": step_achieved / wide_peak, "imads_per_row": imads},
+                    "step": {"achieved": step_achieved / 1e12, "frac": step_achieved / wide_peak, "frac_of_imad32_peak": step_achieved / imad_peak, "imads_per_row": imads_run,
+                             "imads_per_row_reference_count": imads},
                     "hbm": {"achieved": (value / world) * (BYTES_PER_ROW + 2 * 1156) / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": (value / world) * (BYTES_PER_ROW + 2 * 1156) / 1e9 / hbm,
                             "note": "all three kernels: 96 B of inputs/outputs + 1,156 B of scratch written and read once per row; not the bound"},
                     "note": "per GPU; dominant kernel k_dh_ladder: achieved = rows x %d algorithmic 32x32->64 multiply-adds per row of the main loop "
-                            "/ its CUDA-event time; step = all three kernels, rows/s x %d (SURVEY 8d, tight count of decode + DH + encode); peak = "
+                            "/ its CUDA-event time; step = all three kernels, rows/s x %d (SURVEY 8d tight count of decode + DH + encode, less the inversions saved by sharing one between 16 rows); peak = "
                             "IMAD.WIDE.U32 issue rate measured live by fq_imad_peak (32-bit IMAD measured %.2f T/s); HBM is not the bound: "
                             "%d B/row algorithmic + 2.3 KiB/row of scratch -> %.3f of %s %.1f GB/s" % (
-                                IMADS_PER_ROW_LADDER[args.algorithm], imads, imad_peak / 1e12, BYTES_PER_ROW,
+                                IMADS_PER_ROW_LADDER[args.algorithm], imads_run, imad_peak / 1e12, BYTES_PER_ROW,
                                 (value / world) * (BYTES_PER_ROW + 2 * 1156) / 1e9 / hbm, "measured" if peaks else "fallback", hbm)}
         cores = os.cpu_count() or 1
         sample = args.cpu_sample if args.cpu_sample >= 0 else 256 * cores
@@ -348,6 +498,9 @@ def main():
             parity = {"rows_checked": int(m), "bit_exact": True, "checker": "oracle/fourq_oracle.c (DH_windowed restatement, pinned to the reference's golden vectors)",
                       "seconds": time.perf_counter() - t0}
             parity["checker_rows_per_s"] = m / parity["seconds"]      # the C port on all host cores (threads), for scale
+        configs = None
+        if not args.no_configs and rows == ROWS_PER_GPU and world == 1:      # N > 1 runs carry `inproc` instead
+            configs = measure_configs(fq, fqdev, local_rank, wide_peak, hbm, sum(kernel_ms) / len(kernel_ms), args.algorithm, quick=args.quick)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",
@@ -357,8 +510,10 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * rows, "d2h_bytes_per_step": 33 * rows,
                         "note": "fourq_b200.DH(k, B, out=, status=) on pinned numpy arrays (inputs and outputs), wall clock, per GPU bytes"},
+                "e2e_pageable": {"value": e2e_pageable, "unit": UNIT, "frac_of_e2e": e2e_pageable / e2e_value,
+                                 "note": "fourq_b200.DH(k, B) on plain numpy arrays, outputs allocated by the call; the engine stages pageable operands through pinned buffers on its own threads"},
                 "gpu_launches": 3 * args.steps,
-                "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "configs": configs, "inproc": inproc}
     barrier()
     if dist is not None:
         dist.destroy_process_group()

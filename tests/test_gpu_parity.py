@@ -87,14 +87,16 @@ def test_scalar_mult_golden(fq, golden, alg):
 
 
 def test_strict_select_mode_gives_identical_outputs(fq):
-    """fq_set_select_mode: the masked loads (default, predicated LDS) and the strict scan (every lane loads every table
-    entry, SEL per word); every scalar-multiplication kernel must give the same bytes in both modes."""
+    """fq_set_select_mode: the strict scan (default: every lane loads every table entry, SEL per word) and the masked loads
+    (opt-in, predicated LDS); every scalar-multiplication kernel must give the same bytes in both modes."""
     rng = np.random.default_rng(61)
     n = 20000
     k = rng.integers(0, 256, (n, 32), np.uint8)
     pub = fq.MUL_base(rng.integers(0, 256, (n, 32), np.uint8))
     pub[::11] = rng.integers(0, 256, (len(pub[::11]), 32), np.uint8)
     default = fq.get_select_mode()
+    if os.environ.get("FQ_STRICT_SELECT") is None:
+        assert default is True                       # the library default is the strict scan (no digit-dependent memory activity)
     ref = {}
     try:
         for strict in (True, False):
@@ -509,3 +511,78 @@ def test_multi_gpu_slices_match_single(fq):
     for g in range(2, min(fq.device_count(), 8) + 1):
         og, sg = fq.DH(k2, pub, ndev=g)                      # contiguous slices of ceil(n/g) rows, ragged last slice
         assert (og == o1).all() and (sg == s1).all(), g
+
+
+# ---------------------------------------------------------------- round 2 additions
+
+def test_select_and_fp2_invsqrt_golden_and_random(fq, golden):
+    """fq_fp_select / fq_fp2_select / fq_fp2_invsqrt (fields.py:59-64, :236-238, :201-230) against vectors produced by the reference
+    and against the oracle on random rows."""
+    g = golden["select"]
+    for key, cls in (("fp_select", fq.GFp), ("fp2_select", fq.GFp2)):
+        rows = g[key]
+        got = cls.select(np.array([r[0] for r in rows], np.uint8), R([H(r[1]) for r in rows]), R([H(r[2]) for r in rows]))
+        assert hexrows(got) == [r[3] for r in rows]
+    rows = g["fp2_invsqrt"]
+    assert hexrows(fq.GFp2.invsqrt(R([H(r[0]) for r in rows]))) == [r[1] for r in rows]
+    rng = np.random.default_rng(77)
+    n = 100003
+    x = rng.integers(0, 256, (n, 32), np.uint8); y = rng.integers(0, 256, (n, 32), np.uint8)
+    c = rng.integers(0, 2, n, np.uint8)
+    assert (fq.GFp2.select(c, x, y) == np.where(c.reshape(-1, 1) == 1, x, y)).all()
+    x16, y16 = np.ascontiguousarray(x[:, :16]), np.ascontiguousarray(y[:, 16:])
+    assert (fq.GFp.select(c, x16, y16) == np.where(c.reshape(-1, 1) == 1, x16, y16)).all()
+    a = rng.integers(0, 256, (4096, 32), np.uint8)
+    a[::7, 16:] = 0                                                  # the GF(p) branch
+    got = fq.GFp2.invsqrt(a)
+    assert [bytes(r) for r in got] == [O.row_fp2("invsqrt", bytes(r)) for r in a]
+    # where the input is a square the result really is an inverse square root: a * r^2 == 1
+    chk = fq.GFp2.mul(a, fq.GFp2.sqr(got))
+    one = np.zeros(32, np.uint8); one[0] = 1
+    assert (chk == one).all(axis=1).sum() > 1000
+
+
+def test_fp2_inv_shared_inversion_with_zero_rows(fq):
+    """k_fp2_inv_batched: one chain per 16 rows; zeros (in every disguise) inside the groups, ragged sizes."""
+    rng = np.random.default_rng(78)
+    p = O.P127
+    for n in (1, 15, 16, 17, 1023, 70001):
+        a = rng.integers(0, 256, (n, 32), np.uint8)
+        z = rng.random(n) < 0.1
+        a[z] = 0
+        a[rng.random(n) < 0.03] = np.frombuffer(p.to_bytes(16, "little") * 2, np.uint8)          # (p, p) = zero
+        got = fq.GFp2.inv(a)
+        idx = list(range(0, n, max(1, n // 300)))
+        assert [bytes(got[i]) for i in idx] == [O.row_fp2("inv", bytes(a[i])) for i in idx]
+        assert (got[(a == 0).all(axis=1)] == 0).all()
+
+
+def test_pageable_and_pinned_paths_agree_over_many_chunks(fq):
+    """The host engine's staging of pageable inputs/outputs (capi.cu feeder / drainer) against page-locked buffers, on a batch that
+    spans several ramped chunks; also rejects a device pointer as a host buffer."""
+    rng = np.random.default_rng(79)
+    n = 1_300_007
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    pk = fq.pinned_empty((n, 32)); pk[:] = k
+    po = fq.pinned_empty((n, 32))
+    a = fq.MUL_base(k)                      # pageable in, pageable out
+    fq.MUL_base(pk, out=po)                 # pinned in, pinned out
+    b = fq.MUL_base(pk)                     # pinned in, pageable out
+    assert (a == po).all() and (a == b).all()
+    from oracle import c_oracle as C
+    want, _ = C.dh(k[:2048], a[:2048])
+    got, st = fq.DH(k[:2048], a[:2048])
+    assert (got == want).all() and not st.any()
+    from fourq_b200 import _lib, device
+    d = device.DeviceBuffer(0, 64)
+    assert _lib.lib().fq_fp2_sqr(_lib.ptr(k), d.ptr, 2, 1) == _lib.FQ_ERR_ARG
+    assert b"device memory" in _lib.lib().fq_last_error()
+
+
+def test_on_curve_device_op_is_bound(fq):
+    from fourq_b200 import _lib, device
+    assert _lib.DEVOP["on_curve"] == 30
+    xy = R([O.xy_to_bytes(((O.GX), (O.GY))), bytes(64)])
+    d_in = device.DeviceBuffer.from_host(0, xy); d_out = device.DeviceBuffer(0, 2)
+    device.dev_run("on_curve", 0, d_in, None, d_out, None, 2)
+    assert list(d_out.to_host((2,))) == [1, 0]

@@ -20,7 +20,12 @@ template <int NSLOT> struct SelectSlots {
     return S;
   }
 };
-template <int MINB, int NSLOT> __global__ void __launch_bounds__(128, MINB) k_main(const void* k, void* out, size_t n) {
+#ifdef KEXP_MAXNREG
+#define KEXP_BOUNDS(MINB) __maxnreg__(KEXP_MAXNREG)
+#else
+#define KEXP_BOUNDS(MINB) __launch_bounds__(128, MINB)
+#endif
+template <int MINB, int NSLOT> __global__ void KEXP_BOUNDS(MINB) k_main(const void* k, void* out, size_t n) {
   extern __shared__ uint4 smem[];
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   TabView T; T.base = smem + threadIdx.x; T.stride = blockDim.x;
@@ -70,8 +75,12 @@ int main() {
   size_t n = 1 << 20;
   void *k, *out; cudaMalloc(&k, n * 32); cudaMalloc(&out, n * 32);
   cudaMemset(k, 0x5a, n * 32);
+#ifdef KEXP_MAXNREG
+  run<2, 7>("maxnreg 7slots", k, out, n);
+#else
   run<2, 7>("minb2 7slots", k, out, n);
   run<2, 4>("minb2 4slots", k, out, n);
   run<3, 4>("minb3 4slots", k, out, n);
+#endif
   return 0;
 }
