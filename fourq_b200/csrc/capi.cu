@@ -10,8 +10,8 @@
 //   drainer  (one per GPU)  waits for each chunk's completion event in order, copies results that were staged for a
 //                           pageable destination into the caller's memory, collects the kernel time and frees the slot.
 //
-// Three stream slots per GPU keep the H2D of chunk c+1, the kernels of chunk c and the D2H (and host copy-out) of chunk c-1
-// in flight together.  Page-locked caller buffers (fq_host_alloc) are used directly in both directions.  Slot buffers,
+// Four stream slots per GPU (FQ_SLOTS) keep the staging and H2D of the chunks after next, the kernels of chunk c, a chunk queued
+// behind it (so that kernel tails overlap the next chunk's first kernel) and the D2H and host copy-out of chunk c-1 in flight.  Page-locked caller buffers (fq_host_alloc) are used directly in both directions.  Slot buffers,
 // events and streams are created once per GPU and grow on demand; fq_trim wipes and frees them.  There is no CPU
 // implementation of any operation here.
 //
@@ -19,6 +19,7 @@
 // are threads) to exercise exactly this host logic -- chunking, staging, threading, error paths -- without a GPU; that
 // build is test infrastructure and is never shipped or loaded by the product.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -28,6 +29,8 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <sys/mman.h>
+#include <unistd.h>
 #ifdef FQ_MOCK_CUDA
 #include "mock_cuda_runtime.h"
 #else
@@ -38,7 +41,7 @@
 
 namespace {
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 6;                        // stream slots created per GPU; slots_in_use() of them carry chunks
 constexpr int kMaxDev = 16;
 constexpr int kOperands = 5;                      // a, b, c (inputs), out, status
 constexpr size_t kFlushBytes = 256u << 20;        // > 126 MB L2
@@ -152,6 +155,77 @@ std::vector<size_t> chunk_schedule(size_t rows, size_t full) {
   return bounds;
 }
 
+// ---------------------------------------------------------------- host copies of pageable operands
+
+// FQ_COPY_THREADS (1..4, default 3): threads that share one staging copy of a pageable operand.  One core moves 5-10 GB/s,
+// a B200 consumes the 64 B of inputs per DH row at ~6 GB/s and produces 33 B, so a single copying thread per direction is
+// on the critical path (measured: 68 / 73 / 75 M DH rows/s end to end with 1 / 2 / 3 threads before the other changes).
+int copy_threads() {
+  static const int v = [] { const char* e = getenv("FQ_COPY_THREADS"); int x = e ? atoi(e) : 3; return x < 1 ? 1 : x > 4 ? 4 : x; }();
+  return v;
+}
+// Makes the pages of a pageable OUTPUT buffer present and writable without touching their contents (MADV_POPULATE_WRITE,
+// Linux 5.14+; silently skipped where unsupported).  A freshly allocated result array (numpy.empty) otherwise takes its
+// ~8,000 first-touch page faults per 32 MiB inside the drainer's copies, on the critical path of the last chunks.  Called by
+// the thread that is only waiting for the slices anyway, in 4 MiB steps from the start of the buffer (the order of the chunks).
+void populate_output(void* p, size_t bytes) {
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+  static const bool enabled = [] { const char* e = getenv("FQ_POPULATE"); return !(e && e[0] == '0'); }();
+  if (!enabled || !p || bytes < ((size_t)1 << 20)) return;
+  const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+  uintptr_t lo = ((uintptr_t)p + page - 1) / page * page, hi = ((uintptr_t)p + bytes) / page * page;      // whole pages inside the buffer
+  const size_t step = (size_t)4 << 20;
+  for (; lo < hi; lo += step)
+    if (madvise((void*)lo, hi - lo < step ? hi - lo : step, MADV_POPULATE_WRITE) != 0) return;
+}
+// FQ_SLOTS (2..6, default 4): chunks in flight per GPU.  One is being computed, one is queued behind it (so that the tail of a
+// kernel overlaps the next chunk's first kernel), and the others are in host staging on their way in or out.
+int slots_in_use() {
+  static const int v = [] { const char* e = getenv("FQ_SLOTS"); int x = e ? atoi(e) : 4; return x < 2 ? 2 : x > kSlots ? kSlots : x; }();
+  return v;
+}
+bool trace_enabled() {
+  static const bool v = [] { const char* e = getenv("FQ_TRACE"); return e && e[0] == '1'; }();
+  return v;
+}
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// memcpy split between the calling thread and up to three helper threads that sleep between copies
+class CopyHelper {
+ public:
+  void copy(void* dst, const void* src, size_t bytes) {
+    const int parts = bytes >= ((size_t)1 << 20) ? copy_threads() : 1;
+    if (parts == 1) { memcpy(dst, src, bytes); return; }
+    const size_t per = (bytes / parts + 4095) / 4096 * 4096;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      while ((int)threads_ < parts - 1) { std::thread(&CopyHelper::run, this).detach(); threads_++; }
+      for (int i = 1; i < parts; i++) {
+        const size_t lo = (size_t)i * per, hi = lo + per < bytes ? lo + per : bytes;
+        if (lo < hi) { tasks_.push_back({(char*)dst + lo, (const char*)src + lo, hi - lo}); pending_++; }
+      }
+    }
+    cv_.notify_all();
+    memcpy(dst, src, per < bytes ? per : bytes);
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [&] { return pending_ == 0; });
+  }
+ private:
+  struct Task { char* dst; const char* src; size_t n; };
+  void run() {
+    for (;;) {
+      Task t;
+      { std::unique_lock<std::mutex> l(mu_); cv_.wait(l, [&] { return !tasks_.empty(); }); t = tasks_.front(); tasks_.pop_front(); }
+      memcpy(t.dst, t.src, t.n);
+      { std::lock_guard<std::mutex> l(mu_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::mutex mu_; std::condition_variable cv_, done_;
+  std::deque<Task> tasks_; int pending_ = 0; size_t threads_ = 0;
+};
+
 // ---------------------------------------------------------------- per-GPU state
 
 struct SliceJob;
@@ -165,7 +239,7 @@ struct Slot {
   cudaEvent_t e0 = nullptr, e1 = nullptr, done = nullptr;
   bool busy = false;                                    // guarded by DevCtx::smu
 };
-struct Chunk { int si; size_t r0, rows; SliceJob* job; };
+struct Chunk { int si; size_t r0, rows; SliceJob* job; bool last; };
 
 struct DevCtx {
   int dev = 0;
@@ -174,11 +248,13 @@ struct DevCtx {
   Slot slot[kSlots];
   void* flush = nullptr;
   void* comb = nullptr;           // per-digit fixed-base tables (kernels_comb.cu)
+  cudaEvent_t job_e0 = nullptr;   // recorded before the first kernel of a slice job
   int sms = 0;
   // feeder: slice jobs in submission order
   std::mutex qmu; std::condition_variable qcv; std::deque<SliceJob*> jobs; bool threads = false;
   // feeder -> drainer: chunks in enqueue order; also guards Slot::busy and SliceJob::outstanding
   std::mutex smu; std::condition_variable scv; std::deque<Chunk> chunks;
+  CopyHelper copy_in, copy_out;   // staging copies of the feeder / of the drainer
 };
 DevCtx* g_ctx = nullptr;          // kMaxDev contexts, allocated once and never destroyed (their threads are detached)
 std::once_flag g_ctx_once;
@@ -209,6 +285,7 @@ int ctx_init(DevCtx& c) {
       s.e0 = s.e1 = s.done = nullptr; s.st = nullptr;
     }
     if (c.comb) { cudaFree(c.comb); c.comb = nullptr; }
+    if (c.job_e0) { cudaEventDestroy(c.job_e0); c.job_e0 = nullptr; }
   };
 #define CUI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(FQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); undo(); return rc; } } while (0)
   for (int i = 0; i < kSlots; i++) {
@@ -217,6 +294,7 @@ int ctx_init(DevCtx& c) {
     CUI(cudaEventCreate(&s.e0)); CUI(cudaEventCreate(&s.e1));
     CUI(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }
+  CUI(cudaEventCreate(&c.job_e0));
   CUI(fqk_device_init(c.slot[0].st));
   CUI(fqk_comb_init(&c.comb, c.slot[0].st));
   CUI(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, c.dev));
@@ -318,7 +396,8 @@ struct SliceJob {
   CallState* call = nullptr;
   // results
   int rc = FQ_OK; char err[512] = "";
-  float kernel_ms = 0.f;          // sum of the chunks' kernel times (drainer, under smu)
+  double t_stage_in = 0, t_enqueue = 0, t_wait_slot = 0, t_wait_gpu = 0, t_stage_out = 0; int nchunks = 0;      // FQ_TRACE=1 (ms)
+  float kernel_ms = 0.f;          // CUDA-event time from the slice's first kernel to its last (drainer, under smu)
   size_t outstanding = 0;         // chunks handed to the drainer and not yet retired (under smu)
 };
 
@@ -334,9 +413,11 @@ int feed_slice(DevCtx& c, SliceJob* j) {
   int rc = FQ_OK;
   for (size_t ci = 0; ci + 1 < bounds.size() && rc == FQ_OK; ci++) {
     const size_t r0 = j->lo + bounds[ci], rows = bounds[ci + 1] - bounds[ci];
-    const int si = (int)(ci % kSlots);
+    const int si = (int)(ci % slots_in_use());
     Slot& s = c.slot[si];
+    const double tw0 = now_ms();
     { std::unique_lock<std::mutex> l(c.smu); c.scv.wait(l, [&] { return !s.busy; }); if (j->rc != FQ_OK) break; }     // a retired chunk failed: stop feeding
+    j->t_wait_slot += now_ms() - tw0; j->nchunks++;
     if (rows > d.chunk_rows) { rc = fail(FQ_ERR_ARG, "internal: chunk of %zu rows exceeds the staging size %zu", rows, d.chunk_rows); break; }
     auto body = [&]() -> int {
       int e;
@@ -351,20 +432,28 @@ int feed_slice(DevCtx& c, SliceJob* j) {
         const int wb = d.in_bytes[w];
         if (!wb) continue;
         const uint8_t* src = j->in[w] + r0 * wb;
-        if (!j->pinned[w]) { memcpy(s.hbuf[w], src, rows * wb); src = (const uint8_t*)s.hbuf[w]; }     // pageable input: stage here, overlapping earlier chunks' kernels
+        if (!j->pinned[w]) {                          // pageable input: stage here, overlapping earlier chunks' kernels
+          const double t0 = now_ms();
+          c.copy_in.copy(s.hbuf[w], src, rows * wb);
+          j->t_stage_in += now_ms() - t0;
+          src = (const uint8_t*)s.hbuf[w];
+        }
         CU(cudaMemcpyAsync(s.dbuf[w], src, rows * wb, cudaMemcpyHostToDevice, s.st));
       }
+      const double te0 = now_ms();
+      if (ci == 0) CU(cudaEventRecord(c.job_e0, s.st));
       CU(cudaEventRecord(s.e0, s.st));
       CU(launch(c, d.op, s.dbuf[0], s.dbuf[1], s.dbuf[2], s.dbuf[3], s.dbuf[4], rows, s.st, s.scratch));
       CU(cudaEventRecord(s.e1, s.st));
       CU(cudaMemcpyAsync(j->pinned[3] ? (void*)(j->out + r0 * d.out_bytes) : s.hbuf[3], s.dbuf[3], rows * d.out_bytes, cudaMemcpyDeviceToHost, s.st));
       if (d.status) CU(cudaMemcpyAsync(j->pinned[4] ? (void*)(j->status + r0) : s.hbuf[4], s.dbuf[4], rows, cudaMemcpyDeviceToHost, s.st));
       CU(cudaEventRecord(s.done, s.st));
+      j->t_enqueue += now_ms() - te0;
       return FQ_OK;
     };
     rc = body();
     if (rc != FQ_OK) { cudaStreamSynchronize(s.st); break; }      // whatever part of the chunk was enqueued must not outlive its buffers
-    { std::lock_guard<std::mutex> l(c.smu); s.busy = true; j->outstanding++; c.chunks.push_back({si, r0, rows, j}); }
+    { std::lock_guard<std::mutex> l(c.smu); s.busy = true; j->outstanding++; c.chunks.push_back({si, r0, rows, j, ci + 2 == bounds.size()}); }
     c.scv.notify_all();
   }
   if (rc != FQ_OK) job_fail(c, j, rc);
@@ -382,17 +471,20 @@ void drainer_main(DevCtx* cp) {
     Slot& s = c.slot[ch.si];
     SliceJob* j = ch.job;
     const OpDesc& d = j->d;
+    const double tg0 = now_ms();
     cudaError_t e = cudaEventSynchronize(s.done);
+    const double tg1 = now_ms();
     float ms = 0.f;
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.e0, s.e1);
+    if (e == cudaSuccess && ch.last) e = cudaEventElapsedTime(&ms, c.job_e0, s.e1);       // first kernel's start to last kernel's end on this GPU
     if (e != cudaSuccess) {
       cudaGetLastError();
       job_fail(c, j, fail(FQ_ERR_CUDA, "chunk at row %zu on device %d failed: %s", ch.r0, c.dev, cudaGetErrorString(e)));
     } else {
-      if (!j->pinned[3]) memcpy(j->out + ch.r0 * d.out_bytes, s.hbuf[3], ch.rows * d.out_bytes);       // staged results -> caller's pageable memory
+      if (!j->pinned[3]) c.copy_out.copy(j->out + ch.r0 * d.out_bytes, s.hbuf[3], ch.rows * d.out_bytes);       // staged results -> caller's pageable memory
       if (d.status && !j->pinned[4]) memcpy(j->status + ch.r0, s.hbuf[4], ch.rows);
     }
-    { std::lock_guard<std::mutex> l(c.smu); if (e == cudaSuccess) j->kernel_ms += ms; s.busy = false; j->outstanding--; }
+    const double tg2 = now_ms();
+    { std::lock_guard<std::mutex> l(c.smu); if (e == cudaSuccess && ch.last) j->kernel_ms = ms; j->t_wait_gpu += tg1 - tg0; j->t_stage_out += tg2 - tg1; s.busy = false; j->outstanding--; }
     c.scv.notify_all();
   }
 }
@@ -443,7 +535,14 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, const uint8_t* cbuf, ui
     if (k == PK_DEVICE) return fail(FQ_ERR_ARG, "operand %d is device memory: the host entry points take host pointers (use fq_dev_run for device buffers)", w);
     pinned[w] = k == PK_PINNED;
   }
+  bool all_pinned = true;
+  for (int w = 0; w < kOperands; w++) all_pinned = all_pinned && pinned[w];
+  OpDesc dj = d;
+  // Staged (pageable) operands add two host copies to every chunk's trip; shorter chunks shorten what is exposed at both ends
+  // of the pipeline: half the chunk for the variable-base DH ops (measured, one B200: 13.7 -> 12.8 ms per 2^20 rows).
+  if (!all_pinned && is_dh_op(op) && dj.chunk_rows >= 2 * 37888) dj.chunk_rows = dj.chunk_rows / 2 / 128 * 128;
   const size_t per = (n + ndev - 1) / ndev;
+  const double t_call0 = now_ms();
   CallState cs;
   std::vector<SliceJob> jobs((size_t)ndev);
   int used = 0;
@@ -451,7 +550,7 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, const uint8_t* cbuf, ui
     const size_t lo = (size_t)i * per;
     if (lo >= n) break;
     SliceJob& j = jobs[i];
-    j.d = d; j.in[0] = a; j.in[1] = b; j.in[2] = cbuf; j.out = out; j.status = status;
+    j.d = dj; j.in[0] = a; j.in[1] = b; j.in[2] = cbuf; j.out = out; j.status = status;
     j.lo = lo; j.hi = lo + per < n ? lo + per : n;
     for (int w = 0; w < kOperands; w++) j.pinned[w] = pinned[w];
     j.call = &cs;
@@ -459,8 +558,16 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, const uint8_t* cbuf, ui
   }
   { std::lock_guard<std::mutex> l(cs.mu); cs.remaining = used; }
   for (int i = 0; i < used; i++) submit(ctx_of(base + i), &jobs[i]);
+  if (!pinned[3]) populate_output(out, n * (size_t)d.out_bytes);
+  if (d.status && !pinned[4]) populate_output(status, n);
   { std::unique_lock<std::mutex> l(cs.mu); cs.cv.wait(l, [&] { return cs.remaining == 0; }); }
   int rc = FQ_OK;
+  if (trace_enabled()) fprintf(stderr, "[fq trace] op %d: %zu rows on %d device(s), %.3f ms inside the call\n", op, n, used, now_ms() - t_call0);
+  if (trace_enabled())
+    for (int i = 0; i < used; i++)
+      fprintf(stderr, "[fq trace] op %d dev %d rows %zu chunks %d: feeder wait-slot %.2f stage-in %.2f enqueue %.2f ms | drainer wait-gpu %.2f stage-out %.2f ms | kernels %.2f ms | pinned %d%d%d%d%d\n",
+              op, base + i, jobs[i].hi - jobs[i].lo, jobs[i].nchunks, jobs[i].t_wait_slot, jobs[i].t_stage_in, jobs[i].t_enqueue, jobs[i].t_wait_gpu,
+              jobs[i].t_stage_out, jobs[i].kernel_ms, (int)pinned[0], (int)pinned[1], (int)pinned[2], (int)pinned[3], (int)pinned[4]);
   for (int i = 0; i < used; i++) {
     if (jobs[i].rc != FQ_OK && rc == FQ_OK) { rc = jobs[i].rc; snprintf(tl_err, sizeof(tl_err), "%s", jobs[i].err); }
     if (jobs[i].kernel_ms > tl_kernel_ms) tl_kernel_ms = jobs[i].kernel_ms;

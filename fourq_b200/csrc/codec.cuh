@@ -40,7 +40,8 @@ template <bool SPEC = false> FQ_FN u32 pt_decode(const u32* in, fp2& x, fp2& y) 
 
   fp2 y2 = fp2_sqr_c(y);                                                       // :65
   fp2 u = fp2_sub(y2, fp2_one());                                             // :66
-  fp2 v = fp2_add(fp2_mul_c(curve_d(), y2), fp2_one());                         // :67
+  const fp2 dy2 = fp2_mul_c(curve_d(), y2);
+  fp2 v = fp2_add(dy2, fp2_one());                                            // :67
   fpb V0 = fp_prep(v.re), V1 = fp_prep(v.im);
   fp t0 = fp_add(fp_mul_prep(u.re, V0), fp_mul_prep(u.im, V1));               // :69
   fp t1 = fp_sub(fp_mul_prep(u.im, V0), fp_mul_prep(u.re, V1));               // :70
@@ -63,10 +64,12 @@ template <bool SPEC = false> FQ_FN u32 pt_decode(const u32* in, fp2& x, fp2& y) 
   u32 mneg = (pt_sign(x) != s) ? 0xffffffffu : 0u;                            // :88-89
   x = fp2_canon(fp2_select(mneg, fp2_neg(x), x));
   y = fp2_canon(y);
-  // :91-94.  conj does not change x^2's norm part only its sign of the imaginary part; both candidates are tested
-  bool on1 = pt_on_curve(x, y);
+  // :91-94: PointOnCurve (curve4q.py:23-29) of both candidates, x and conj(x).  y^2 and d y^2 are at hand from :65-67 and
+  // conj(x)^2 = conj(x^2), so the two tests -x^2 + y^2 == 1 + (d y^2) x^2 cost one squaring and two multiplications.
+  const fp2 x2 = fp2_sqr_c(x), x2c = fp2_conj(x2);
+  bool on1 = fp2_eq(fp2_sub(y2, x2), fp2_add(fp2_one(), fp2_mul_c(dy2, x2)));
   fp2 xc = fp2_canon(fp2_conj(x));
-  bool on2 = pt_on_curve(xc, y);
+  bool on2 = fp2_eq(fp2_sub(y2, x2c), fp2_add(fp2_one(), fp2_mul_c(dy2, x2c)));
   x = fp2_select(on1 ? 0xffffffffu : 0u, x, xc);
   if (st == FQ_ST_OK && !(on1 | on2)) st = FQ_ST_NOT_ON_CURVE;
   return st;

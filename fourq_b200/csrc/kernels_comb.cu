@@ -43,11 +43,11 @@ k_comb(const u32* __restrict__ tabs, const void* __restrict__ k, DhScratch sc, s
 cudaError_t fqk_comb_init(void** tabs_out, cudaStream_t s) {
   cudaError_t e;
   u32* tabs = nullptr;
-  if ((e = cudaMalloc(&tabs, 2 * FQ_COMB_WORDS * sizeof(u32))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_comb<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_comb<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_comb<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_comb<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_COMB_WORDS * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&tabs, 2 * FQ_COMB_WORDS * sizeof(u32))) != cudaSuccess) return e;      // freed on every error path below
   k_comb_build<<<(2 * FQ_COMB_DIGITS + 63) / 64, 64, 0, s>>>(tabs);
   if ((e = cudaGetLastError()) != cudaSuccess) { cudaFree(tabs); return e; }
   if ((e = cudaStreamSynchronize(s)) != cudaSuccess) { cudaFree(tabs); return e; }

@@ -1,14 +1,18 @@
-// kio.cuh -- 128-bit row loads/stores shared by the kernels: a thread owns one row; a warp touches 1 KiB contiguous.
+// kio.cuh -- row loads/stores shared by the kernels.  A thread owns one 32-byte row and moves it with ONE 256-bit access
+// (LDG.E.256 / STG.E.256, sm_100+): a warp request covers 1 KiB of contiguous memory and every 32-byte sector it touches is used
+// in full by that one request.  64-byte affine rows are two such accesses.  Rows must be 32-byte aligned (cudaMalloc'd buffers
+// and the engine's staging buffers are).
 #pragma once
 #include "rows.cuh"
 
 __device__ __forceinline__ void ld8(const void* base, size_t row, u32* w) {
-  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * row;
-  uint4 a = p[0], b = p[1];
-  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  const char* p = reinterpret_cast<const char*>(base) + 32 * row;
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
 __device__ __forceinline__ void st8(void* base, size_t row, const u32* w) {
-  uint4* p = reinterpret_cast<uint4*>(base) + 2 * row;
-  p[0] = make_uint4(w[0], w[1], w[2], w[3]); p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  char* p = reinterpret_cast<char*>(base) + 32 * row;
+  asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               :: "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "l"(p) : "memory");
 }
 static inline unsigned grid_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }

@@ -91,15 +91,20 @@ FQ_FN ptR1 pt_add(const ptR1& Q, const ptR2& S) { return pt_add_core(pt_r1_to_r3
 
 // Out-of-line copies of the group law for the once-per-row setup code (see fp2.cuh); operands pass through memory.
 struct ptR3 { fp2 N, D, E, F; };        // R3 = (X+Y, Y-X, Z, T), not prepared
-FQ_CALL void pt_dbl_c(ptR1* Q) { ptR1 q = *Q; pt_dbl(q); *Q = q; }
-FQ_CALL void pt_r1_to_r3_c(ptR3* R, const ptR1* P) {                                     // curve4q.py:119-126
-  R->N = fp2_add(P->X, P->Y); R->D = fp2_sub(P->Y, P->X); R->E = P->Z; R->F = fp2_mul(P->Ta, P->Tb);
+FQ_CALL ptR1 pt_dbl_v(ptR1 q) { pt_dbl(q); return q; }
+FQ_FN void pt_dbl_c(ptR1* Q) { *Q = pt_dbl_v(*Q); }
+FQ_FN void pt_r1_to_r3_c(ptR3* R, const ptR1* P) {                                     // curve4q.py:119-126
+  R->N = fp2_add(P->X, P->Y); R->D = fp2_sub(P->Y, P->X); R->E = P->Z; R->F = fp2_mul_c(P->Ta, P->Tb);
 }
-FQ_CALL void pt_add_core_c(ptR1* out, const ptR3* P, const ptR2* S) {                    // curve4q.py:155-171
-  ptR3p Pp; Pp.N = fp2_prep(P->N); Pp.D = fp2_prep(P->D); Pp.E = fp2_prep(P->E); Pp.F = fp2_prep(P->F);
-  *out = pt_add_core(Pp, *S);
+FQ_CALL ptR1 pt_add_core_v(ptR3 P, ptR2 S) {
+  ptR3p Pp; Pp.N = fp2_prep(P.N); Pp.D = fp2_prep(P.D); Pp.E = fp2_prep(P.E); Pp.F = fp2_prep(P.F);
+  return pt_add_core(Pp, S);
 }
-FQ_CALL void pt_r1_to_r2_c(ptR2* R, const ptR1* P) { *R = pt_r1_to_r2(*P); }             // curve4q.py:109-116
+FQ_FN void pt_add_core_c(ptR1* out, const ptR3* P, const ptR2* S) { *out = pt_add_core_v(*P, *S); }
+FQ_FN void pt_r1_to_r2_c(ptR2* R, const ptR1* P) {
+  R->N = fp2_add(P->X, P->Y); R->D = fp2_sub(P->Y, P->X); R->E = fp2_dbl(P->Z);
+  R->F = fp2_mul_c(fp2_mul_c(P->Ta, P->Tb), curve_2d());
+}
 
 // curve4q.py:450-455.  [392]P = 8 * 49 P: DBL, ADD, 4 DBL, ADD, 3 DBL
 FQ_FN ptR1 pt_clear_cofactor(const fp2& x, const fp2& y) {

@@ -6,17 +6,13 @@
 #include "kernels.h"
 #include "x25519.cuh"
 #include "batchinv.cuh"
+#include "kio.cuh"
 
-static __device__ __forceinline__ void ld8x(const void* base, size_t row, u32* w) {
-  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * row;
-  uint4 a = p[0], b = p[1];
-  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-}
 __global__ void __launch_bounds__(128) k_x25519(const void* __restrict__ k, const void* __restrict__ u, uint4* __restrict__ scratch, size_t npad, size_t n) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   u32 kw[8], uw[8];
-  ld8x(k, row, kw); ld8x(u, row, uw);
+  ld8(k, row, kw); ld8(u, row, uw);
   f25 x2, z2;
   x25519_ladder(kw, uw, x2, z2);
   st_f25(scratch + row, npad, x2); st_f25(scratch + 2 * npad + row, npad, z2);

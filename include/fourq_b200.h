@@ -55,7 +55,8 @@ FQ_API int fq_device_count(void);                 /* >= 0, or FQ_ERR_NO_DEVICE *
 FQ_API const char* fq_last_error(void);
 /* GPUs used by the host entry points are first .. first+ndev-1 (default 0).  One process per GPU sets its LOCAL_RANK. */
 FQ_API int fq_set_device_base(int first);
-/* kernel-only milliseconds (CUDA events, max over devices of the per-device sum) of the last host call of this thread */
+/* device milliseconds of the last host call of this thread: CUDA-event time from the first kernel to the end of the last kernel of
+ * a GPU's slice (its chunks overlap: copies of one run under the kernels of another), maximum over the GPUs used */
 FQ_API float fq_last_kernel_ms(void);
 
 /* Constant-time table selection of every scalar multiplication (csrc/dh.cuh).  In both modes every thread issues the loads

@@ -18,6 +18,8 @@ def main():
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot_inst = 0
     for r in rd:
+        if r and r[0] == "Kernel Name":          # a report may hold several tables (launches / views) of the kernel: keep the first
+            break
         if len(r) < len(hdr):
             continue
         m = re.match(r"\s*(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ix["Source"]])
