@@ -47,7 +47,10 @@ __device__ __forceinline__ void stq(uint4* p, const fp& a) { *p = make_uint4(a.v
 __device__ __forceinline__ fp ldq(const uint4* p) { uint4 w = *p; return fp_set(w.x, w.y, w.z, w.w); }
 
 // three CTAs per SM with the endomorphisms (a fourth would spill), four without (measured: 3.26 vs 3.47 ms, 2.15 vs 2.21 ms)
-template <bool AFFINE, bool ENDO> __global__ void __launch_bounds__(FQ_DH_THREADS, ENDO ? 3 : 4)
+#ifndef FQ_PREP_MINB_ENDO
+#define FQ_PREP_MINB_ENDO 3
+#endif
+template <bool AFFINE, bool ENDO> __global__ void __launch_bounds__(FQ_DH_THREADS, ENDO ? FQ_PREP_MINB_ENDO : 4)
 k_dh_prep(const void* __restrict__ k, const void* __restrict__ pt, DhScratch sc, size_t n) {
   const size_t row = (size_t)blockIdx.x * FQ_DH_THREADS + threadIdx.x;
   const size_t src = row < n ? row : n - 1;          // tail threads recompute the last row (their scratch slots exist)
