@@ -289,9 +289,12 @@ def measure_inproc(fq, world, algorithm, quick=False):
     page-locked host arrays, wall clock, best of 3; every multi-GPU result is compared byte for byte with the ndev = 1 result."""
     res = {"n_gpus": world}
     fq.set_device(0)
+    from fourq_b200 import _lib
+    res["gpu_numa_nodes"] = [int(_lib.lib().fq_device_numa_node(i)) for i in range(world)]
     n4 = 1 << (20 if quick else 24)
-    pk = fq.pinned_empty((n4, 32)); pk[:] = np.random.default_rng(5).integers(0, 256, (n4, 32), np.uint8)
-    po1 = fq.pinned_empty((n4, 32)); poN = fq.pinned_empty((n4, 32))
+    # arrays laid out for `world` GPUs: each GPU's slice of rows sits on that GPU's NUMA node where the platform allows it
+    pk = fq.pinned_empty((n4, 32), ndev=world); pk[:] = np.random.default_rng(5).integers(0, 256, (n4, 32), np.uint8)
+    po1 = fq.pinned_empty((n4, 32), ndev=world); poN = fq.pinned_empty((n4, 32), ndev=world)
 
     def best(fn, reps=3):
         fn()
@@ -307,9 +310,9 @@ def measure_inproc(fq, world, algorithm, quick=False):
                    "ndevN_max_device_kernel_ms": kN, "scaling": "strong", "parity_vs_ndev1": same4}
     rows = (1 << (18 if quick else 20))
     n3 = rows * world
-    k3 = fq.pinned_empty((n3, 32)); k3[:] = np.random.default_rng(3).integers(0, 256, (n3, 32), np.uint8)
-    p3 = fq.pinned_empty((n3, 32)); p3[:] = poN[:n3] if n3 <= n4 else np.tile(poN, ((n3 + n4 - 1) // n4, 1))[:n3]
-    o3 = fq.pinned_empty((n3, 32)); s3 = fq.pinned_empty((n3,))
+    k3 = fq.pinned_empty((n3, 32), ndev=world); k3[:] = np.random.default_rng(3).integers(0, 256, (n3, 32), np.uint8)
+    p3 = fq.pinned_empty((n3, 32), ndev=world); p3[:] = poN[:n3] if n3 <= n4 else np.tile(poN, ((n3 + n4 - 1) // n4, 1))[:n3]
+    o3 = fq.pinned_empty((n3, 32), ndev=world); s3 = fq.pinned_empty((n3,), ndev=world)
     tN3 = best(lambda: fq.DH(k3, p3, out=o3, status=s3, ndev=world, algorithm=algorithm))
     m = min(n3, 1 << 18)                                 # a slice that crosses the first slice boundary when world > 4; ndev = 1 on the same rows
     lo = max(0, rows - m // 2)

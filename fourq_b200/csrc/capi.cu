@@ -4,7 +4,7 @@
 // exchange step, hence no collective).  Every GPU has its own pair of host threads and its own lock, so slices of one
 // call run concurrently and callers on disjoint GPUs do not wait for each other:
 //
-//   feeder   (one per GPU)  takes the slice, cuts it into chunks (ramped schedule, see chunk_schedule) and for each chunk
+//   feeder   (one per GPU)  takes chunks of its slice (ramped sizes; other slices' rows once its own are gone: CallWork) and for each chunk
 //                           waits for a free stream slot, copies pageable inputs into the slot's pinned staging buffers,
 //                           and enqueues H2D copies, the kernels and the D2H copies on the slot's stream;
 //   drainer  (one per GPU)  waits for each chunk's completion event in order, copies results that were staged for a
@@ -30,7 +30,9 @@
 #include <thread>
 #include <vector>
 #include <sys/mman.h>
+#include <sys/syscall.h>
 #include <unistd.h>
+#include <utility>
 #ifdef FQ_MOCK_CUDA
 #include "mock_cuda_runtime.h"
 #else
@@ -49,6 +51,7 @@ constexpr size_t kFlushBytes = 256u << 20;        // > 126 MB L2
 thread_local char tl_err[512] = "";
 thread_local float tl_kernel_ms = 0.f;
 thread_local float tl_phase_ms[3] = {0.f, 0.f, 0.f};
+thread_local size_t tl_rows_per_dev[16] = {0};      // rows each GPU of the last host call of this thread ended up processing
 std::atomic<int> g_dev_base{0};
 std::atomic<int> g_strict{-1};    // table selection: 1 = strict scan (default), 0 = masked loads, -1 = not yet read from FQ_STRICT_SELECT
 
@@ -120,6 +123,17 @@ size_t scratch_bytes(int op, size_t rows) {
   return is_comb_op(op) ? fqk_comb_scratch_bytes(rows) : op == FQ_DEVOP_X25519 ? fqk_x25519_scratch_bytes(rows) : fqk_dh_scratch_bytes(rows);
 }
 
+// Operations whose big multi-GPU calls adapt their slices to the measured speed of each GPU (FQ_ADAPT=0: always equal slices).
+// On a host where some GPUs reach the caller's memory more slowly than others, equal slices end with the slowest GPU.
+int rate_class(int op) {
+  static const bool on = [] { const char* e = getenv("FQ_ADAPT"); return !(e && e[0] == '0'); }();
+  if (!on) return -1;
+  if (op == FQ_DEVOP_DH || op == FQ_DEVOP_DH_AFFINE) return 0;
+  if (op == FQ_DEVOP_DH_ENDO || op == FQ_DEVOP_DH_ENDO_AFFINE) return 1;
+  if (op == FQ_DEVOP_MUL_BASE_COMB || op == FQ_DEVOP_DH_BASE_COMB) return 2;
+  return -1;
+}
+
 int strict_mode() {
   int v = g_strict.load();
   if (v < 0) {                                     // first use: the environment decides unless fq_set_select_mode got there first
@@ -130,30 +144,80 @@ int strict_mode() {
   return v;
 }
 
-// Chunk schedule of one slice (the same for every device): ramp up from a small chunk (doubling) so that the first kernels
-// start after a short copy, full chunks in the middle, ramp down by halves so that little work and a short copy-back remain
-// exposed at the end.  Slices of at most two small chunks are not split.  No chunk exceeds `full` rows (the staging buffers
-// are sized for exactly that).  bounds[c] .. bounds[c+1] are the rows of chunk c.
-std::vector<size_t> chunk_schedule(size_t rows, size_t full) {
-  std::vector<size_t> bounds;
-  size_t small = full / 8 >= 16384 ? full / 8 : 16384;
-  if (small > full) small = full;
-  const bool ramp = ramp_enabled() && rows > 2 * small;
-  size_t pos = 0, sz = ramp ? small : full;
-  bounds.push_back(0);
-  while (pos < rows) {
-    const size_t left = rows - pos;
-    size_t take = sz < left ? sz : left;
-    if (ramp && left > small && left <= 2 * take) {              // ramp down by halves, in units of 128 rows
-      take = (left / 2 + 127) / 128 * 128;
-      if (take > full) take = full;
-      if (take > left) take = left;
+// Work of one call.  The rows are cut into one contiguous slice per GPU (slice i = rows [i*ceil(n/ndev), ...)); a GPU works
+// through its own slice from the front in chunks, and when that is exhausted it takes chunks from the BACK of the slice
+// that has the most rows left.  With equal GPUs nothing is ever stolen and every GPU handles exactly its slice; on a host
+// whose GPUs do not all reach memory at the same speed (measured on an 8 x B200 virtual machine: four of the eight take
+// 8-13 % longer for the same slice, and the machine exposes no NUMA information to place buffers by) the call ends when the
+// work is done instead of when the slowest slice is.
+//
+// Chunk sizes of a slice: ramp up from a small chunk (doubling) so that the first kernels start after a short copy, full
+// chunks in the middle, ramp down by halves so that little work and a short copy-back remain exposed at the end.  Slices of
+// at most two small chunks are not split.  No chunk exceeds `full` rows (the staging buffers are sized for exactly that).
+struct CallWork {
+  std::mutex mu;
+  struct Range { size_t lo, hi; bool ramp; };
+  std::vector<Range> r;               // rows of each slice not yet handed out
+  size_t full = 0, small = 0;
+  bool steal = true, abort = false;
+  // share: optional relative speeds of the GPUs (rows per ms of their last calls); null or incomplete -> equal slices
+  void init(size_t n, int ndev, size_t full_rows, const double* share = nullptr) {
+    full = full_rows;
+    small = full / 8 >= 16384 ? full / 8 : 16384;
+    if (small > full) small = full;
+    static const bool steal_on = [] { const char* e = getenv("FQ_STEAL"); return !(e && e[0] == '0'); }();
+    steal = steal_on;
+    const size_t per = (n + (size_t)ndev - 1) / (size_t)ndev;
+    double total = 0;
+    bool weighted = share != nullptr && ndev > 1 && n >= (size_t)ndev * 2 * full;
+    for (int i = 0; weighted && i < ndev; i++) { if (share[i] > 0) total += share[i]; else weighted = false; }
+    double f[64], fsum = 0;                                 // proportional to the measured speed, within +-25 % of the equal share
+    for (int i = 0; weighted && i < ndev && i < 64; i++) {
+      f[i] = share[i] / total * ndev;
+      f[i] = f[i] < 0.75 ? 0.75 : f[i] > 1.25 ? 1.25 : f[i];
+      fsum += f[i];
     }
-    pos += take; bounds.push_back(pos);
-    if (sz < full) sz = sz * 2 < full ? sz * 2 : full;
+    size_t lo = 0;
+    for (int i = 0; i < ndev; i++) {
+      size_t len = per;
+      if (weighted) {
+        len = (size_t)((double)n * f[i] / fsum) / 128 * 128;
+        if (i == ndev - 1) len = n - lo;
+      }
+      const size_t hi = lo + len < n ? lo + len : n;
+      r.push_back({lo, i == ndev - 1 && weighted ? n : hi, ramp_enabled() && hi - lo > 2 * small});
+      lo = hi;
+    }
   }
-  return bounds;
-}
+  // the next chunk for GPU `me`, which has taken `taken` chunks of this call so far; false when no rows are left
+  bool take(int me, int taken, size_t* r0, size_t* rows) {
+    std::lock_guard<std::mutex> l(mu);
+    if (abort) return false;
+    Range& own = r[(size_t)me];
+    if (own.lo < own.hi) {
+      const size_t left = own.hi - own.lo;
+      size_t sz = full;
+      if (own.ramp) { sz = small; for (int t = 0; t < taken && sz < full; t++) sz = sz * 2 < full ? sz * 2 : full; }
+      size_t n = sz < left ? sz : left;
+      if (own.ramp && left > small && left <= 2 * n) {              // ramp down by halves, in units of 128 rows
+        n = (left / 2 + 127) / 128 * 128;
+        if (n > full) n = full;
+        if (n > left) n = left;
+      }
+      *r0 = own.lo; *rows = n; own.lo += n;
+      return true;
+    }
+    if (!steal) return false;
+    size_t best = r.size(), most = 0;
+    for (size_t j = 0; j < r.size(); j++) if (r[j].hi - r[j].lo > most) { most = r[j].hi - r[j].lo; best = j; }
+    if (best == r.size()) return false;
+    size_t n = most;                                                 // a victim's last piece goes whole; otherwise half of what it has left
+    if (most > small) { n = (most / 2 + 127) / 128 * 128; if (n > full) n = full; if (n > most) n = most; }
+    r[best].hi -= n; *r0 = r[best].hi; *rows = n;
+    return true;
+  }
+  void stop() { std::lock_guard<std::mutex> l(mu); abort = true; }
+};
 
 // ---------------------------------------------------------------- host copies of pageable operands
 
@@ -239,7 +303,7 @@ struct Slot {
   cudaEvent_t e0 = nullptr, e1 = nullptr, done = nullptr;
   bool busy = false;                                    // guarded by DevCtx::smu
 };
-struct Chunk { int si; size_t r0, rows; SliceJob* job; bool last; };
+struct Chunk { int si; size_t r0, rows; SliceJob* job; };
 
 struct DevCtx {
   int dev = 0;
@@ -255,6 +319,8 @@ struct DevCtx {
   // feeder -> drainer: chunks in enqueue order; also guards Slot::busy and SliceJob::outstanding
   std::mutex smu; std::condition_variable scv; std::deque<Chunk> chunks;
   CopyHelper copy_in, copy_out;   // staging copies of the feeder / of the drainer
+  std::atomic<double> rate[3];    // rows per ms this GPU sustained in its last big calls, per class of operation (rate_class); 0 = unknown
+  DevCtx() { for (auto& x : rate) x.store(0.0); }
 };
 DevCtx* g_ctx = nullptr;          // kMaxDev contexts, allocated once and never destroyed (their threads are detached)
 std::once_flag g_ctx_once;
@@ -389,9 +455,10 @@ struct CallState { std::mutex mu; std::condition_variable cv; int remaining = 0;
 
 struct SliceJob {
   OpDesc d;
-  const uint8_t* in[3] = {nullptr, nullptr, nullptr};      // whole-call buffers; the slice is rows [lo, hi)
+  const uint8_t* in[3] = {nullptr, nullptr, nullptr};      // whole-call buffers
   uint8_t* out = nullptr; uint8_t* status = nullptr;
-  size_t lo = 0, hi = 0;
+  CallWork* work = nullptr; int index = 0;                 // the call's rows and this GPU's slice number
+  size_t rows_done = 0;
   bool pinned[kOperands] = {true, true, true, true, true};
   CallState* call = nullptr;
   // results
@@ -402,22 +469,21 @@ struct SliceJob {
 };
 
 void job_fail(DevCtx& c, SliceJob* j, int rc) {       // first error of a job wins; tl_err holds the text of this thread's failure
-  std::lock_guard<std::mutex> l(c.smu);
-  if (j->rc == FQ_OK) { j->rc = rc; snprintf(j->err, sizeof(j->err), "%s", tl_err); }
+  { std::lock_guard<std::mutex> l(c.smu); if (j->rc == FQ_OK) { j->rc = rc; snprintf(j->err, sizeof(j->err), "%s", tl_err); } }
+  if (j->work) j->work->stop();                        // the call has failed: the other GPUs stop taking chunks
 }
 
 // feeder side of one slice; caller holds c.mu and the device is current
 int feed_slice(DevCtx& c, SliceJob* j) {
   const OpDesc& d = j->d;
-  const std::vector<size_t> bounds = chunk_schedule(j->hi - j->lo, d.chunk_rows);
   int rc = FQ_OK;
-  for (size_t ci = 0; ci + 1 < bounds.size() && rc == FQ_OK; ci++) {
-    const size_t r0 = j->lo + bounds[ci], rows = bounds[ci + 1] - bounds[ci];
-    const int si = (int)(ci % slots_in_use());
+  size_t r0 = 0, rows = 0;
+  for (int ci = 0; rc == FQ_OK && j->work->take(j->index, ci, &r0, &rows); ci++) {
+    const int si = ci % slots_in_use();
     Slot& s = c.slot[si];
     const double tw0 = now_ms();
     { std::unique_lock<std::mutex> l(c.smu); c.scv.wait(l, [&] { return !s.busy; }); if (j->rc != FQ_OK) break; }     // a retired chunk failed: stop feeding
-    j->t_wait_slot += now_ms() - tw0; j->nchunks++;
+    j->t_wait_slot += now_ms() - tw0; j->nchunks++; j->rows_done += rows;
     if (rows > d.chunk_rows) { rc = fail(FQ_ERR_ARG, "internal: chunk of %zu rows exceeds the staging size %zu", rows, d.chunk_rows); break; }
     auto body = [&]() -> int {
       int e;
@@ -453,7 +519,7 @@ int feed_slice(DevCtx& c, SliceJob* j) {
     };
     rc = body();
     if (rc != FQ_OK) { cudaStreamSynchronize(s.st); break; }      // whatever part of the chunk was enqueued must not outlive its buffers
-    { std::lock_guard<std::mutex> l(c.smu); s.busy = true; j->outstanding++; c.chunks.push_back({si, r0, rows, j, ci + 2 == bounds.size()}); }
+    { std::lock_guard<std::mutex> l(c.smu); s.busy = true; j->outstanding++; c.chunks.push_back({si, r0, rows, j}); }
     c.scv.notify_all();
   }
   if (rc != FQ_OK) job_fail(c, j, rc);
@@ -475,7 +541,7 @@ void drainer_main(DevCtx* cp) {
     cudaError_t e = cudaEventSynchronize(s.done);
     const double tg1 = now_ms();
     float ms = 0.f;
-    if (e == cudaSuccess && ch.last) e = cudaEventElapsedTime(&ms, c.job_e0, s.e1);       // first kernel's start to last kernel's end on this GPU
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, c.job_e0, s.e1);       // first kernel's start to this chunk's end on this GPU: the last chunk's value stays
     if (e != cudaSuccess) {
       cudaGetLastError();
       job_fail(c, j, fail(FQ_ERR_CUDA, "chunk at row %zu on device %d failed: %s", ch.r0, c.dev, cudaGetErrorString(e)));
@@ -484,7 +550,7 @@ void drainer_main(DevCtx* cp) {
       if (d.status && !j->pinned[4]) memcpy(j->status + ch.r0, s.hbuf[4], ch.rows);
     }
     const double tg2 = now_ms();
-    { std::lock_guard<std::mutex> l(c.smu); if (e == cudaSuccess && ch.last) j->kernel_ms = ms; j->t_wait_gpu += tg1 - tg0; j->t_stage_out += tg2 - tg1; s.busy = false; j->outstanding--; }
+    { std::lock_guard<std::mutex> l(c.smu); if (e == cudaSuccess) j->kernel_ms = ms; j->t_wait_gpu += tg1 - tg0; j->t_stage_out += tg2 - tg1; s.busy = false; j->outstanding--; }
     c.scv.notify_all();
   }
 }
@@ -541,17 +607,20 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, const uint8_t* cbuf, ui
   // Staged (pageable) operands add two host copies to every chunk's trip; shorter chunks shorten what is exposed at both ends
   // of the pipeline: half the chunk for the variable-base DH ops (measured, one B200: 13.7 -> 12.8 ms per 2^20 rows).
   if (!all_pinned && is_dh_op(op) && dj.chunk_rows >= 2 * 37888) dj.chunk_rows = dj.chunk_rows / 2 / 128 * 128;
-  const size_t per = (n + ndev - 1) / ndev;
   const double t_call0 = now_ms();
   CallState cs;
+  CallWork work;
+  const int rc_class = rate_class(op);
+  double share[kMaxDev] = {0};
+  if (rc_class >= 0) for (int i = 0; i < ndev; i++) share[i] = ctx_of(base + i).rate[rc_class].load();
+  work.init(n, ndev, dj.chunk_rows, rc_class >= 0 ? share : nullptr);
   std::vector<SliceJob> jobs((size_t)ndev);
   int used = 0;
   for (int i = 0; i < ndev; i++) {
-    const size_t lo = (size_t)i * per;
-    if (lo >= n) break;
-    SliceJob& j = jobs[i];
+    if (work.r[(size_t)i].lo >= work.r[(size_t)i].hi) break;          // fewer rows than GPUs: the empty slices get no job
+    SliceJob& j = jobs[(size_t)i];
     j.d = dj; j.in[0] = a; j.in[1] = b; j.in[2] = cbuf; j.out = out; j.status = status;
-    j.lo = lo; j.hi = lo + per < n ? lo + per : n;
+    j.work = &work; j.index = i;
     for (int w = 0; w < kOperands; w++) j.pinned[w] = pinned[w];
     j.call = &cs;
     used++;
@@ -566,8 +635,17 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, const uint8_t* cbuf, ui
   if (trace_enabled())
     for (int i = 0; i < used; i++)
       fprintf(stderr, "[fq trace] op %d dev %d rows %zu chunks %d: feeder wait-slot %.2f stage-in %.2f enqueue %.2f ms | drainer wait-gpu %.2f stage-out %.2f ms | kernels %.2f ms | pinned %d%d%d%d%d\n",
-              op, base + i, jobs[i].hi - jobs[i].lo, jobs[i].nchunks, jobs[i].t_wait_slot, jobs[i].t_stage_in, jobs[i].t_enqueue, jobs[i].t_wait_gpu,
+              op, base + i, jobs[i].rows_done, jobs[i].nchunks, jobs[i].t_wait_slot, jobs[i].t_stage_in, jobs[i].t_enqueue, jobs[i].t_wait_gpu,
               jobs[i].t_stage_out, jobs[i].kernel_ms, (int)pinned[0], (int)pinned[1], (int)pinned[2], (int)pinned[3], (int)pinned[4]);
+  for (int i = 0; i < kMaxDev; i++) tl_rows_per_dev[i] = i < used ? jobs[(size_t)i].rows_done : 0;
+  if (rc_class >= 0 && ndev > 1)                       // remember how fast each GPU was (rows per ms of device time), for the next call's slices
+    for (int i = 0; i < used; i++) {
+      const SliceJob& j = jobs[(size_t)i];
+      if (j.rc != FQ_OK || j.kernel_ms <= 0.f || j.rows_done < 2 * dj.chunk_rows) continue;
+      std::atomic<double>& r = ctx_of(base + i).rate[rc_class];
+      const double now = (double)j.rows_done / j.kernel_ms, old = r.load();
+      r.store(old > 0 ? 0.5 * (old + now) : now);
+    }
   for (int i = 0; i < used; i++) {
     if (jobs[i].rc != FQ_OK && rc == FQ_OK) { rc = jobs[i].rc; snprintf(tl_err, sizeof(tl_err), "%s", jobs[i].err); }
     if (jobs[i].kernel_ms > tl_kernel_ms) tl_kernel_ms = jobs[i].kernel_ms;
@@ -590,6 +668,32 @@ int slot_wipe_free(Slot& s) {
   if (s.scratch) { CU(cudaFree(s.scratch)); s.scratch = nullptr; s.scratch_cap = 0; }
   return FQ_OK;
 }
+
+// ---------------------------------------------------------------- page-locked memory placed next to the GPUs that will read it
+// On a multi-socket host a GPU moves data to and from the other socket's memory through the inter-socket link: measured on
+// an 8 x B200 box, the four GPUs that are remote to a buffer take 8 % (keygen) to 13 % (DH) longer for their slices than the
+// four local ones, and the call ends with the slowest.  fq_host_alloc_sliced lays a buffer out the way run_host will cut it:
+// the bytes of slice i are placed (mbind, MPOL_PREFERRED) on the NUMA node of GPU base + i before the pages are locked.
+// Everything here degrades silently to an ordinary page-locked allocation: no NUMA information (a VM that hides it), no
+// permission for mbind (a container's seccomp profile), a single node.
+int device_numa_node(int dev) {
+#ifdef FQ_MOCK_CUDA
+  (void)dev; return -1;
+#else
+  char id[32] = "";
+  if (cudaDeviceGetPCIBusId(id, sizeof(id), dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* q = id; *q; q++) if (*q >= 'A' && *q <= 'F') *q = (char)(*q - 'A' + 'a');
+  char path[96]; snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", id);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+#endif
+}
+std::mutex g_sliced_mu;
+std::vector<std::pair<void*, size_t>> g_sliced;     // allocations of fq_host_alloc_sliced: base, mapped length
 
 // locks the context of GPU `dev` for a device-resident call of the calling thread
 struct DevLock {
@@ -683,7 +787,52 @@ int fq_host_alloc(void** p, size_t bytes) {
   CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
   return FQ_OK;
 }
-int fq_host_free(void* p) { if (p) CU(cudaFreeHost(p)); return FQ_OK; }
+int fq_host_alloc_sliced(void** p, size_t rows, size_t row_bytes, int ndev) {
+  if (!p || ndev < 1 || row_bytes == 0) return fail(FQ_ERR_ARG, "null pointer / bad slice description");
+  const int count = device_count();
+  if (count < 0) return count;
+  const int base = g_dev_base.load();
+  const size_t page = (size_t)sysconf(_SC_PAGESIZE), bytes = rows * row_bytes;
+  const size_t len = ((bytes ? bytes : 1) + page - 1) / page * page;
+  void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (m == MAP_FAILED) return fail(FQ_ERR_CUDA, "mmap of %zu bytes failed", len);
+#ifdef __linux__
+  const size_t per = (rows + ndev - 1) / ndev;
+  for (int i = 0; i < ndev && base + i < count; i++) {
+    size_t lo = (size_t)i * per * row_bytes, hi = ((size_t)(i + 1) * per < rows ? (size_t)(i + 1) * per : rows) * row_bytes;
+    if (lo >= hi) break;
+    lo = (lo + page - 1) / page * page; hi = hi / page * page;           // whole pages of the slice (a straddling page goes where it falls)
+    const int node = device_numa_node(base + i);
+    if (node < 0 || node >= 1024 || lo >= hi) continue;
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(237 /* SYS_mbind */, (char*)m + lo, hi - lo, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(8 * sizeof(mask) + 1), 0u);      // best effort
+  }
+#endif
+  cudaError_t e = cudaHostRegister(m, len, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { munmap(m, len); return fail(FQ_ERR_CUDA, "cudaHostRegister of %zu bytes failed: %s", len, cudaGetErrorString(e)); }
+  { std::lock_guard<std::mutex> l(g_sliced_mu); g_sliced.push_back({m, len}); }
+  *p = m;
+  return FQ_OK;
+}
+int fq_host_free(void* p) {
+  if (!p) return FQ_OK;
+  size_t len = 0;
+  {
+    std::lock_guard<std::mutex> l(g_sliced_mu);
+    for (size_t i = 0; i < g_sliced.size(); i++) if (g_sliced[i].first == p) { len = g_sliced[i].second; g_sliced.erase(g_sliced.begin() + (long)i); break; }
+  }
+  if (len) { CU(cudaHostUnregister(p)); munmap(p, len); return FQ_OK; }
+  CU(cudaFreeHost(p));
+  return FQ_OK;
+}
+// NUMA node of a GPU as the kernel reports it (/sys/bus/pci/devices/<bus id>/numa_node), -1 if unknown
+int fq_device_numa_node(int dev) {
+  const int count = device_count();
+  if (count < 0) return count;
+  if (dev < 0 || dev >= count) return fail(FQ_ERR_ARG, "device %d out of range (%d device(s))", dev, count);
+  return device_numa_node(dev);
+}
 
 int fq_dev_alloc(int dev, void** p, size_t bytes) {
   DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
@@ -733,6 +882,11 @@ int fq_dev_run3(int op, int dev, const void* a, const void* b, const void* c, vo
 int fq_dev_run(int op, int dev, const void* a, const void* b, void* out, void* status, size_t n, int iters, float* ms) {
   return fq_dev_run3(op, dev, a, b, nullptr, out, status, n, iters, ms);
 }
+int fq_last_rows_per_device(size_t* rows, int ndev) {
+  if (!rows || ndev < 1) return fail(FQ_ERR_ARG, "null pointer");
+  for (int i = 0; i < ndev; i++) rows[i] = i < kMaxDev ? tl_rows_per_dev[i] : 0;
+  return FQ_OK;
+}
 int fq_dev_last_phase_ms(float* ms3) {
   if (!ms3) return fail(FQ_ERR_ARG, "null pointer");
   for (int i = 0; i < 3; i++) ms3[i] = tl_phase_ms[i];
@@ -776,9 +930,20 @@ int fq_imad_peak(int dev, double* wide_per_s, double* imad32_per_s) {
 }
 
 #ifdef FQ_MOCK_CUDA
+// test hook (tests/hostsim builds only): the slices of a call of n rows on ndev GPUs with the given relative speeds
+FQ_API int fq_test_slices(size_t n, int ndev, size_t full, const double* share, size_t* lo, size_t* hi) {
+  CallWork w;
+  w.init(n, ndev, full, share);
+  for (int i = 0; i < ndev; i++) { lo[i] = w.r[(size_t)i].lo; hi[i] = w.r[(size_t)i].hi; }
+  return (int)w.r.size();
+}
 // test hook (tests/hostsim builds only): the chunk schedule of a slice of `rows` rows with full chunks of `full` rows
 FQ_API size_t fq_test_chunk_schedule(size_t rows, size_t full, size_t* bounds, size_t cap) {
-  const std::vector<size_t> b = chunk_schedule(rows, full);
+  CallWork w;
+  w.init(rows, 1, full);
+  std::vector<size_t> b(1, 0);
+  size_t r0 = 0, n = 0;
+  for (int ci = 0; w.take(0, ci, &r0, &n); ci++) b.push_back(r0 + n);
   for (size_t i = 0; i < b.size() && i < cap; i++) bounds[i] = b[i];
   return b.size();
 }

@@ -36,14 +36,25 @@ def trim():
     _lib.check(_lib.lib().fq_trim())
 
 
+def last_rows_per_device(ndev):
+    """Rows each of the ndev GPUs processed in the last host call of this thread (equal slices unless a GPU ran out early and helped)."""
+    rows = (ctypes.c_size_t * ndev)()
+    _lib.check(_lib.lib().fq_last_rows_per_device(rows, ndev))
+    return [int(x) for x in rows]
+
+
 def last_kernel_ms():
     return float(_lib.lib().fq_last_kernel_ms())
 
 
 class _Pinned:
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, rows=None, row_bytes=None, ndev=1):
         self.ptr = ctypes.c_void_p()
-        _lib.check(_lib.lib().fq_host_alloc(ctypes.byref(self.ptr), nbytes))
+        if ndev > 1 and rows and _lib.lib().fq_host_alloc_sliced(ctypes.byref(self.ptr), rows, row_bytes, ndev) == _lib.FQ_OK:
+            pass                      # laid out for ndev GPUs
+        else:                         # one GPU, or the platform refused the placement (e.g. no host registration): ordinary page-locked memory
+            self.ptr = ctypes.c_void_p()
+            _lib.check(_lib.lib().fq_host_alloc(ctypes.byref(self.ptr), nbytes))
         self.nbytes = nbytes
 
     def __del__(self):
@@ -58,10 +69,14 @@ class _PinnedArray(np.ndarray):
     _fq_owner = None
 
 
-def pinned_empty(shape, dtype=np.uint8):
-    """numpy array backed by page-locked host memory (cudaHostAlloc): host entry points then copy without staging."""
+def pinned_empty(shape, dtype=np.uint8, ndev=1):
+    """numpy array backed by page-locked host memory: host entry points then copy without staging.  ndev > 1: the array is
+    laid out for a call on ndev GPUs -- the bytes of GPU i's slice of rows are placed on that GPU's NUMA node
+    (fq_host_alloc_sliced; an ordinary page-locked array where the platform does not allow it)."""
+    shape = tuple(shape) if isinstance(shape, (tuple, list)) else (int(shape),)
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    owner = _Pinned(max(nbytes, 1))
+    row_bytes = (nbytes // shape[0]) if shape and shape[0] else 0
+    owner = _Pinned(max(nbytes, 1), rows=shape[0] if shape else 0, row_bytes=row_bytes, ndev=ndev)
     buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(owner.ptr.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape).view(_PinnedArray)
     arr._fq_owner = owner

@@ -11,8 +11,8 @@
  *       encoded point     32 B                                   (curve4q.py:41-46)
  *       scalar            32 B  little-endian unsigned, no clamping (curve4q.py:558-559 limb order)
  *   - host entry points take HOST pointers (pageable or pinned) and run on `ndev` GPUs, rows split in contiguous
- *     slices (device i gets rows [i*ceil(n/ndev), ...)); there is no collective and no CPU fallback: with no CUDA
- *     device every call returns FQ_ERR_NO_DEVICE.
+ *     slices (device i starts on rows [i*ceil(n/ndev), ...) and, once done, helps with the back of the slice that has the
+ *     most rows left); there is no collective and no CPU fallback: with no CUDA device every call returns FQ_ERR_NO_DEVICE.
  *   - return value: 0 (FQ_OK) or a negative FQ_ERR_*; fq_last_error() gives the text (thread-local).
  *   - per-row outcome in status[n] (uint8): see FQ_ST_*.  Rows that fail are zero-filled in the output.
  *   - thread-safe: every GPU has its own lock and its own pair of host threads (one feeds chunks to the GPU, one retires
@@ -58,6 +58,10 @@ FQ_API int fq_set_device_base(int first);
 /* device milliseconds of the last host call of this thread: CUDA-event time from the first kernel to the end of the last kernel of
  * a GPU's slice (its chunks overlap: copies of one run under the kernels of another), maximum over the GPUs used */
 FQ_API float fq_last_kernel_ms(void);
+/* rows[i] = rows GPU first+i processed in the last host call of this thread.  Every GPU starts on its own contiguous slice of
+ * ceil(n/ndev) rows; one that runs out takes chunks from the back of the slice with the most rows left, so on a host whose GPUs
+ * do not all reach memory equally fast the numbers differ from n/ndev. */
+FQ_API int fq_last_rows_per_device(size_t* rows, int ndev);
 
 /* Constant-time table selection of every scalar multiplication (csrc/dh.cuh).  In both modes every thread issues the loads
  * of ALL table entries from digit-independent addresses and there is no secret-dependent branch.
@@ -153,6 +157,12 @@ FQ_API int fq_trim(void);
 /* ---- pinned host memory for zero-staging transfers (optional; any host pointer is accepted above) */
 FQ_API int fq_host_alloc(void** p, size_t bytes);
 FQ_API int fq_host_free(void* p);
+/* Page-locked array of `rows` rows of `row_bytes` bytes for a batch that will run on `ndev` GPUs: the bytes of slice i (rows
+ * [i*ceil(rows/ndev), ...), the way the host entry points cut a batch) are placed on the NUMA node of GPU i before the pages
+ * are locked, so that every GPU copies from and to its own socket's memory.  Falls back to an ordinary page-locked allocation
+ * where the platform gives no NUMA information or does not permit the placement.  Free with fq_host_free. */
+FQ_API int fq_host_alloc_sliced(void** p, size_t rows, size_t row_bytes, int ndev);
+FQ_API int fq_device_numa_node(int dev);          /* the NUMA node of a GPU, -1 if the platform does not say */
 
 /* ---- device-resident variants, for measurement with inputs already in HBM (bench.py `value`, ncu).
  * op: one of FQ_DEVOP_*; pointers are device pointers on GPU `dev`; the kernel is launched `iters` times back to back on

@@ -23,9 +23,10 @@ struct Globals {
   std::deque<MockStream*> streams;
   int devices = 2;
   std::atomic<int> jitter_us{0}, expect_zero_free{0};
+  std::atomic<int> kernel_delay_us[16];             // extra time of every kernel task on a device (a slow GPU / a slow link)
   std::atomic<long> violations{0}, memcpy_bytes{0}, kernel_tasks{0};
 };
-Globals& G() { static Globals* g = new Globals; return *g; }     // never destroyed: stream threads outlive static destructors
+Globals& G() { static Globals* g = [] { Globals* x = new Globals; for (auto& d : x->kernel_delay_us) d.store(0); return x; }(); return *g; }     // never destroyed: stream threads outlive static destructors
 thread_local int tl_device = 0;
 thread_local cudaError_t tl_last = cudaSuccess;
 
@@ -57,6 +58,7 @@ struct MockStream {
   bool busy = false, stop = false;
   std::thread th;
   std::minstd_rand rng{12345};
+  int device = tl_device;
   MockStream() { th = std::thread([this] { run(); }); }
   void run() {
     for (;;) {
@@ -83,7 +85,11 @@ struct MockEvent {
   Clock::time_point t;
 };
 
-void mock_stream_enqueue(cudaStream_t s, std::function<void()> fn) { G().kernel_tasks++; s->push(std::move(fn)); }
+void mock_stream_enqueue(cudaStream_t s, std::function<void()> fn) {
+  G().kernel_tasks++;
+  const int us = G().kernel_delay_us[s->device & 15].load();
+  if (us > 0) s->push([fn, us] { std::this_thread::sleep_for(std::chrono::microseconds(us)); fn(); }); else s->push(std::move(fn));
+}
 
 const char* cudaGetErrorString(cudaError_t e) {
   switch (e) {
@@ -182,6 +188,19 @@ cudaError_t cudaMalloc(void** p, size_t bytes) { return alloc(p, bytes, cudaMemo
 cudaError_t cudaFree(void* p) { return release(p, cudaMemoryTypeDevice); }
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return alloc(p, bytes, cudaMemoryTypeHost, "cudaHostAlloc"); }
 cudaError_t cudaFreeHost(void* p) { return release(p, cudaMemoryTypeHost); }
+cudaError_t cudaHostRegister(void* p, size_t bytes, unsigned) {
+  if (inject("cudaHostRegister")) return ret(cudaErrorUnknown);
+  std::lock_guard<std::mutex> l(G().mu); G().allocs[(uintptr_t)p] = {bytes, cudaMemoryTypeHost, tl_device};
+  return cudaSuccess;
+}
+cudaError_t cudaHostUnregister(void* p) {
+  sync_all();
+  std::lock_guard<std::mutex> l(G().mu);
+  auto it = G().allocs.find((uintptr_t)p);
+  if (it == G().allocs.end()) { G().violations++; return ret(cudaErrorInvalidValue); }
+  G().allocs.erase(it);
+  return cudaSuccess;
+}
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t s) {
   if (inject("cudaMemcpyAsync")) return ret(cudaErrorUnknown);
   if (!range_ok(dst, bytes) || !range_ok(src, bytes)) { G().violations++; return ret(cudaErrorInvalidValue); }
@@ -218,6 +237,7 @@ __attribute__((visibility("default"))) void mock_set_device_count(int n) { std::
 // the nth call from now of `api` fails (1 = the next one; 0 clears)
 __attribute__((visibility("default"))) void mock_fail_nth(const char* api, int nth) { std::lock_guard<std::mutex> l(G().mu); if (nth > 0) G().fail_nth[api] = nth; else G().fail_nth.erase(api); }
 __attribute__((visibility("default"))) void mock_set_jitter_us(int us) { G().jitter_us.store(us); }
+__attribute__((visibility("default"))) void mock_set_kernel_delay_us(int dev, int us) { G().kernel_delay_us[dev & 15].store(us); }
 __attribute__((visibility("default"))) long mock_violations() { return G().violations.load(); }
 __attribute__((visibility("default"))) long mock_memcpy_bytes() { return G().memcpy_bytes.load(); }
 // live allocations of a type (2 = device, 1 = pinned host) and their total size

@@ -17,7 +17,7 @@ struct cudaDeviceProp { int multiProcessorCount; };
 struct MockStream; struct MockEvent;
 typedef MockStream* cudaStream_t;
 typedef MockEvent* cudaEvent_t;
-enum { cudaStreamNonBlocking = 1, cudaHostAllocPortable = 1, cudaEventDisableTiming = 2 };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocPortable = 1, cudaEventDisableTiming = 2, cudaHostRegisterPortable = 1 };
 
 const char* cudaGetErrorString(cudaError_t e);
 cudaError_t cudaGetLastError();
@@ -39,6 +39,8 @@ cudaError_t cudaMalloc(void** p, size_t bytes);
 cudaError_t cudaFree(void* p);
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned flags);
 cudaError_t cudaFreeHost(void* p);
+cudaError_t cudaHostRegister(void* p, size_t bytes, unsigned flags);
+cudaError_t cudaHostUnregister(void* p);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s);
 cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t s);

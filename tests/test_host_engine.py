@@ -127,6 +127,78 @@ def test_three_input_select_through_the_engine(eng):
     assert (out16 == np.where(c.reshape(-1, 1) == 1, x16, y16)).all()
 
 
+def test_sliced_pinned_allocation_is_page_locked_and_freed(eng, sim):
+    """fq_host_alloc_sliced: the NUMA placement is best effort (nothing to observe on this box), but the array must be
+    page-locked over its whole length, usable by a multi-GPU call without staging, and released by fq_host_free."""
+    n = 300_001
+    before = eng.mock_live_allocs(1, None)
+    bufs = []
+    for _ in range(3):
+        p = ctypes.c_void_p()
+        assert eng.fq_host_alloc_sliced(ctypes.byref(p), n, 32, 4) == 0, eng.fq_last_error()
+        bufs.append((np.frombuffer((ctypes.c_uint8 * (n * 32)).from_address(p.value), np.uint8).reshape(n, 32), p))
+    (a, ha), (b, hb), (o, ho) = bufs
+    assert eng.mock_is_pinned(ha) and eng.mock_is_pinned(ctypes.c_void_p(ha.value + n * 32 - 1))
+    rng = np.random.default_rng(12)
+    a[:] = rng.integers(0, 256, (n, 32), np.uint8); b[:] = rng.integers(0, 256, (n, 32), np.uint8); o[:] = 0
+    staged = eng.mock_memcpy_bytes()
+    assert eng.fq_fp2_sub(ha, hb, ho, n, 4) == 0, eng.fq_last_error()
+    assert eng.mock_memcpy_bytes() - staged == 3 * n * 32                 # H2D of a and b, D2H of out: no staging copies in between
+    ref = np.empty_like(a)
+    sim.sim_fp2_op(4, P(a), P(b), P(ref), ctypes.c_size_t(n))
+    assert (o == ref).all()
+    del a, b, o, bufs
+    for h in (ha, hb, ho):
+        assert eng.fq_host_free(h) == 0
+    assert eng.mock_live_allocs(1, None) == before and eng.mock_violations() == 0
+    assert eng.fq_host_alloc_sliced(None, 4, 32, 1) == _lib.FQ_ERR_ARG
+
+
+def test_slices_follow_the_measured_speeds(eng):
+    """CallWork::init: equal contiguous slices by default; with known speeds the slices are proportional (within +-25 % of the equal
+    share, multiples of 128 rows) and still cover every row exactly once."""
+    eng.fq_test_slices.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
+    for n, ndev, full in ((1 << 24, 8, 303104), (8 << 20, 8, 454656), (1000, 4, 454656), (3, 8, 128), (1 << 22, 2, 454656)):
+        lo = (ctypes.c_size_t * ndev)(); hi = (ctypes.c_size_t * ndev)()
+        for share in (None, [225.5] * (ndev // 2) + [209.0] * (ndev - ndev // 2), [1.0] + [100.0] * (ndev - 1), [0.0] * ndev):
+            sh = (ctypes.c_double * ndev)(*share) if share else None
+            assert eng.fq_test_slices(n, ndev, full, sh, lo, hi) == ndev
+            assert lo[0] == 0 and hi[ndev - 1] == n and all(hi[i] == lo[i + 1] for i in range(ndev - 1)) and all(lo[i] <= hi[i] for i in range(ndev))
+            per = (n + ndev - 1) // ndev
+            lens = [hi[i] - lo[i] for i in range(ndev)]
+            if share is None or not all(share) or n < ndev * 2 * full:
+                assert lens == [max(0, min(per, n - i * per)) for i in range(ndev)]
+            else:
+                assert all(0.65 * n / ndev <= x <= 1.30 * n / ndev + 128 * ndev for x in lens), lens
+                assert all(x % 128 == 0 for x in lens[:-1])
+                if share[0] > share[-1]:
+                    assert lens[0] > lens[-1]
+
+
+def test_a_slow_gpu_gets_help_from_the_others(eng, sim):
+    """Work stealing between slices (capi.cu CallWork): with one GPU much slower than the rest, the others finish their own slices
+    and take rows from the back of the slow one's; the bytes are the same as with equal slices."""
+    rng = np.random.default_rng(13)
+    n = 8_000_003                                   # slices of 2 M rows: more than the four chunks a GPU keeps in flight
+    a = rng.integers(0, 256, (n, 32), np.uint8); out = np.zeros_like(a)
+    ref = np.empty_like(a)
+    sim.sim_fp2_op(5, P(a), None, P(ref), ctypes.c_size_t(n))
+    rows = (ctypes.c_size_t * 4)()
+    assert eng.fq_fp2_neg(P(a), P(out), n, 4) == 0
+    assert eng.fq_last_rows_per_device(rows, 4) == 0 and sum(rows) == n
+    eng.mock_set_kernel_delay_us(2, 60000)                       # GPU 2: 60 ms extra per kernel
+    try:
+        out[:] = 0
+        assert eng.fq_fp2_neg(P(a), P(out), n, 4) == 0, eng.fq_last_error()
+    finally:
+        eng.mock_set_kernel_delay_us(2, 0)
+    assert (out == ref).all()
+    assert eng.fq_last_rows_per_device(rows, 4) == 0 and sum(rows) == n
+    per = (n + 3) // 4
+    assert rows[2] < per and max(rows[0], rows[1], rows[3]) > per, list(rows)
+    assert eng.mock_violations() == 0
+
+
 def test_argument_errors(eng):
     a = np.zeros((4, 32), np.uint8); out = np.zeros_like(a)
     assert eng.fq_fp2_sqr(P(a), P(out), 4, 0) == _lib.FQ_ERR_ARG
