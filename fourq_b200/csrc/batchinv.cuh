@@ -26,29 +26,37 @@
 //   void emit(int j, elem zi, u32 zero)    consume 1 / z_j
 template <class OPS, class IO> FQ_FN void batch_invert(IO& io, int R) {
   typedef typename OPS::elem elem;
+  // Both passes are software-pipelined: the loads of the next row are issued before the multiplications of this one (the rows of
+  // a thread are `stride` rows apart, so every load is a trip to L2 or HBM that would otherwise sit on the dependency chain).
+  u32 zero, zero_next = 0;
+  elem z_next = io.z(0, zero_next);
   elem acc = OPS::one();
   FQ_NOUNROLL
   for (int j = 0; j < R; j++) {
-    u32 zero;
-    elem z = io.z(j, zero);
+    elem z = z_next;
+    if (j + 1 < R) z_next = io.z(j + 1, zero_next);
     acc = (j == 0) ? z : OPS::mul(acc, z);
     if (j + 1 < R) io.park(j, acc);
   }
   elem inv = OPS::inv(acc);
+  z_next = io.z(R - 1, zero_next);
+  elem p_next = R > 1 ? io.parked(R - 2) : OPS::one();
   FQ_NOUNROLL
   for (int j = R - 1; j >= 0; j--) {
-    u32 zero;
-    elem z = io.z(j, zero);
+    elem z = z_next, p = p_next;
+    zero = zero_next;
+    if (j > 0) { z_next = io.z(j - 1, zero_next); if (j > 1) p_next = io.parked(j - 2); }
     elem zi = inv;
-    if (j > 0) { zi = OPS::mul(inv, io.parked(j - 1)); inv = OPS::mul(inv, z); }
+    if (j > 0) { zi = OPS::mul(inv, p); inv = OPS::mul(inv, z); }
     io.emit(j, zi, zero);
   }
 }
 
+// multiplications inlined: a real call would make the prefetched loads wait at the call boundary
 struct Fp2Ops {
   typedef fp2 elem;
   static FQ_MFN fp2 one() { return fp2_one(); }
-  static FQ_MFN fp2 mul(const fp2& a, const fp2& b) { return fp2_mul_c(a, b); }
+  static FQ_MFN fp2 mul(const fp2& a, const fp2& b) { return fp2_mul(a, b); }
   static FQ_MFN fp2 inv(const fp2& a) { return fp2_inv(a); }
 };
 
@@ -108,7 +116,8 @@ template <bool AFFINE, bool CHECK_NEUTRAL> struct FinishIO {
     const size_t row = t + (size_t)j * stride;
     if (row >= n) return;
     const fp2 X = fp2_set(ldq4(R + row), ldq4(R + npad + row)), Y = fp2_set(ldq4(R + 2 * npad + row), ldq4(R + 3 * npad + row));
-    const fp2 ox = fp2_canon(fp2_mul_c(X, zi)), oy = fp2_canon(fp2_mul_c(Y, zi));                   // curve4q.py:103-106
+    const fp2b Zi = fp2_prep(zi);
+    const fp2 ox = fp2_canon(fp2_mul_prep(X, Zi)), oy = fp2_canon(fp2_mul_prep(Y, Zi));                   // curve4q.py:103-106
     u32 st = meta[row] >> 8;
     const bool neutral = fp2_eq_canon(ox, fp2_zero()) & fp2_eq_canon(oy, fp2_one());                // curve4q.py:459
     if (CHECK_NEUTRAL && st == FQ_ST_OK && neutral) st = FQ_ST_NEUTRAL;

@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """Small end-to-end pass over every kernel family on ragged sizes, every output compared with the C oracle.
-Written to run under compute-sanitizer (`compute-sanitizer --tool memcheck python tools/allkernels_check.py`); the sanitizer
+Written to run under compute-sanitizer (`compute-sanitizer --tool memcheck python tests/checks/allkernels_check.py`); the sanitizer
 is closed on this round's GPU pool (it answered rc=86), so it serves as a quick all-kernels parity pass:
-    python tools/allkernels_check.py"""
+    python tests/checks/allkernels_check.py"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import fourq_b200 as fq                     # noqa: E402
 from oracle import c_oracle as C            # noqa: E402
@@ -43,6 +43,13 @@ for op in ("mul", "add", "sub"):
     assert (getattr(fq.GFp, op)(a[:, :16], b[:, :16]) == C.fp(op, a[:, :16], b[:, :16])).all()
 for op in ("sqr", "inv", "neg", "invsqrt"):
     assert (getattr(fq.GFp, op)(a[:, :16]) == C.fp(op, a[:, :16])).all()
-u = fq.x25519(k, a)                          # k_x25519
-assert u.shape == (n, 32)
+from oracle import fourq_oracle as O        # noqa: E402
+c = rng.integers(0, 2, n, np.uint8)
+assert (fq.GFp2.select(c, a, b) == np.where(c.reshape(-1, 1) == 1, a, b)).all()                  # k_select<2>
+assert (fq.GFp.select(c, a[:, :16], b[:, :16]) == np.where(c.reshape(-1, 1) == 1, a[:, :16], b[:, :16])).all()   # k_select<1>
+a2 = a.copy(); a2[::5, 16:] = 0
+assert [bytes(r) for r in fq.GFp2.invsqrt(a2)] == [O.row_fp2("invsqrt", bytes(r)) for r in a2]   # k_fp2_invsqrt
+assert (fq.curve4q.PointOnCurve(xy) == (st == 0)).all()                                          # k_on_curve (failed rows are zero-filled: off the curve)
+u = fq.x25519(k, a)                          # k_x25519 + k_x25519_finish
+assert [bytes(r) for r in u[:64]] == [O.x25519(bytes(k[i]), bytes(a[i])) for i in range(64)]
 print("allkernels_check: all kernels ran, outputs match the C oracle")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Secondary measurements for BASELINE.json configs 2, 4 and 5 (bench.py is config 3, the headline).
 
-    python tools/bench_configs.py [--gpus N] [--quick] > profiles/rNN_configs.jsonl
+    python tests/checks/bench_configs.py [--gpus N] [--quick] > profiles/rNN_configs.jsonl
 
 One JSON line per measurement: kernel-only time with device-resident inputs (CUDA events, best of 5 after 2 warm-ups, L2
 flushed between launches) and, where it makes sense, the end-to-end rate through the public API from pinned host arrays.
@@ -20,7 +20,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import fourq_b200 as fq                       # noqa: E402

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Soak run: N random rows (default 2^24) through every scalar-multiplication path, every row compared with the C oracle.
-    python tools/soak.py [log2_rows] > profiles/rNN_soak.json"""
+    python tests/checks/soak.py [log2_rows] > profiles/rNN_soak.json"""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import fourq_b200 as fq                     # noqa: E402
 from oracle import c_oracle as C            # noqa: E402

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""X25519 soak: 65,536 random (k, u) rows on the GPU against the Python oracle (all host cores).  python tools/x25519_soak.py"""
+"""X25519 soak: 65,536 random (k, u) rows on the GPU against the Python oracle (all host cores).  python tests/checks/x25519_soak.py"""
 import sys, os, numpy as np, multiprocessing as mp
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import fourq_b200 as fq
 from oracle import fourq_oracle as O
 def f(a): return O.x25519(a[0], a[1])

@@ -7,8 +7,8 @@ bash tools/profile_run.sh $TAG 2> gpurun_out/profile_run.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2>/dev/null
 FQ_STRICT_SELECT=1 python bench.py --steps 10 --warmup 3 --cpu-sample 0 --verify-rows 0 > gpurun_out/bench_${TAG}_endo_strict.json 2>/dev/null
 FQ_STRICT_SELECT=1 python bench.py --algorithm windowed --steps 10 --warmup 3 --cpu-sample 0 --verify-rows 0 > gpurun_out/bench_${TAG}_win_strict.json 2>/dev/null
-python tools/bench_configs.py > gpurun_out/configs_${TAG}.jsonl 2> gpurun_out/configs_${TAG}.err
-FQ_STRICT_SELECT=1 python tools/bench_configs.py > gpurun_out/configs_${TAG}_strict.jsonl 2>> gpurun_out/configs_${TAG}.err
+python tests/checks/bench_configs.py > gpurun_out/configs_${TAG}.jsonl 2> gpurun_out/configs_${TAG}.err
+FQ_STRICT_SELECT=1 python tests/checks/bench_configs.py > gpurun_out/configs_${TAG}_strict.jsonl 2>> gpurun_out/configs_${TAG}.err
 python tools/ct_timing.py > gpurun_out/ct_timing_masked.jsonl 2>/dev/null
 FQ_STRICT_SELECT=1 python tools/ct_timing.py > gpurun_out/ct_timing_strict.jsonl 2>/dev/null
-python tools/allkernels_check.py
+python tests/checks/allkernels_check.py
