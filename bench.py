@@ -305,20 +305,23 @@ def measure_inproc(fq, world, algorithm, quick=False):
     t1 = best(lambda: fq.MUL_base(pk, out=po1, ndev=1))
     tN = best(lambda: fq.MUL_base(pk, out=poN, ndev=world))
     kN = fq.last_kernel_ms()
+    from fourq_b200 import device as fqdev
+    rows4 = fqdev.last_rows_per_device(world)          # the engine cuts later calls' slices by each GPU's measured speed, and idle GPUs steal
     same4 = bool((po1 == poN).all())
     res["cfg4"] = {"rows": n4, "ndev1_rows_per_s": n4 / t1, "ndevN_rows_per_s": n4 / tN, "ndev1_ms": t1 * 1e3, "ndevN_ms": tN * 1e3, "speedup": t1 / tN,
-                   "ndevN_max_device_kernel_ms": kN, "scaling": "strong", "parity_vs_ndev1": same4}
+                   "ndevN_max_device_span_ms": kN, "ndevN_rows_per_device": rows4, "scaling": "strong", "parity_vs_ndev1": same4}
     rows = (1 << (18 if quick else 20))
     n3 = rows * world
     k3 = fq.pinned_empty((n3, 32), ndev=world); k3[:] = np.random.default_rng(3).integers(0, 256, (n3, 32), np.uint8)
     p3 = fq.pinned_empty((n3, 32), ndev=world); p3[:] = poN[:n3] if n3 <= n4 else np.tile(poN, ((n3 + n4 - 1) // n4, 1))[:n3]
     o3 = fq.pinned_empty((n3, 32), ndev=world); s3 = fq.pinned_empty((n3,), ndev=world)
     tN3 = best(lambda: fq.DH(k3, p3, out=o3, status=s3, ndev=world, algorithm=algorithm))
+    rows3 = fqdev.last_rows_per_device(world)
     m = min(n3, 1 << 18)                                 # a slice that crosses the first slice boundary when world > 4; ndev = 1 on the same rows
     lo = max(0, rows - m // 2)
     o1, s1 = fq.DH(k3[lo:lo + m], p3[lo:lo + m], ndev=1, algorithm=algorithm)
     same3 = bool((o1 == o3[lo:lo + m]).all() and (s1 == s3[lo:lo + m]).all())
-    res["cfg3"] = {"rows": n3, "rows_per_s": n3 / tN3, "ms": tN3 * 1e3, "scaling": "weak", "parity_vs_ndev1": same3, "parity_rows": int(m)}
+    res["cfg3"] = {"rows": n3, "rows_per_s": n3 / tN3, "ms": tN3 * 1e3, "rows_per_device": rows3, "scaling": "weak", "parity_vs_ndev1": same3, "parity_rows": int(m)}
     res["parity_vs_ndev1"] = same4 and same3
     res["note"] = ("one process drives all GPUs through fq_mul_base_comb / fq_dh_endo with ndev = %d (contiguous slices, per-device feeder and drainer "
                    "threads, no collective); pinned host arrays, wall clock of the whole call, best of 3" % world)

@@ -38,7 +38,7 @@ def main():
         t = best(lambda: fq.MUL_base(pk, out=o, ndev=g))
         t1 = t1 or t
         print(json.dumps({"config": "cfg4 fixed-base keygen, 2^24 rows, strong scaling", "ndev": g, "ms": t * 1e3, "rows_per_s": n4 / t, "speedup_vs_ndev1": t1 / t,
-                          "device_span_ms": fq.last_kernel_ms(), "parity_vs_ndev1": bool((o == ref).all())}), flush=True)
+                          "device_span_ms": fq.last_kernel_ms(), "rows_per_device": fq.device.last_rows_per_device(g), "parity_vs_ndev1": bool((o == ref).all())}), flush=True)
     rows = 1 << 20
     e1 = None
     for g in ns:
@@ -48,12 +48,12 @@ def main():
         pub = fq.pinned_empty((n3, 32), ndev=gg); pub[:] = ref[:n3]
         o = fq.pinned_empty((n3, 32), ndev=gg); s = fq.pinned_empty((n3,), ndev=gg)
         t = best(lambda: fq.DH(k, pub, out=o, status=s, ndev=g))
-        span = fq.last_kernel_ms()
+        span = fq.last_kernel_ms(); rpd = fq.device.last_rows_per_device(g)
         e1 = e1 or rows / t
         o1, s1 = fq.DH(k[rows - 65536:rows + 65536] if g > 1 else k[:131072], ref[rows - 65536:rows + 65536] if g > 1 else ref[:131072], ndev=1)
         got = o[rows - 65536:rows + 65536] if g > 1 else o[:131072]
         print(json.dumps({"config": "cfg3 variable-base DH, 2^20 rows per GPU, weak scaling", "ndev": g, "ms": t * 1e3, "rows_per_s": n3 / t, "scaling_vs_ndev1": n3 / t / e1,
-                          "device_span_ms": span, "parity_vs_ndev1": bool((o1 == got).all()) and not s.any()}), flush=True)
+                          "device_span_ms": span, "rows_per_device": rpd, "parity_vs_ndev1": bool((o1 == got).all()) and not s.any()}), flush=True)
 
 
 if __name__ == "__main__":

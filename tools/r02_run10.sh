@@ -20,3 +20,7 @@ for f in ("gpurun_out/r10_bench_endo.json","gpurun_out/r10_bench_win.json"):
     print(f, "%.2f Mrows/s  %.3f ms  ladder frac %.4f step %.4f e2e %.2f  pageable %.2f (%.3f)  kernels %s" % (d["value"]/1e6, d["ms_per_step"], r["frac"], r["step"]["frac"], d["e2e"]["value"]/1e6, d["e2e_pageable"]["value"]/1e6, d["e2e_pageable"]["frac_of_e2e"], r["kernel_ms"]))
 print(open("gpurun_out/r10_bench_reference.json").read()[:400])
 PY
+echo "== affine-table ladder experiment"; timeout 120 ./tools/kexp/ml_affine
+echo "== strict ladder reference"; timeout 120 ./tools/kexp/ml_strict255
+echo "== compute-sanitizer attempt"; timeout 300 compute-sanitizer --tool memcheck python tests/checks/allkernels_check.py > gpurun_out/r10_sanitizer.log 2>&1; echo "sanitizer rc=$?"; tail -5 gpurun_out/r10_sanitizer.log
+timeout 120 python tests/checks/allkernels_check.py
