@@ -240,6 +240,8 @@ void populate_output(void* p, size_t bytes) {
   if (!enabled || !p || bytes < ((size_t)1 << 20)) return;
   const size_t page = (size_t)sysconf(_SC_PAGESIZE);
   uintptr_t lo = ((uintptr_t)p + page - 1) / page * page, hi = ((uintptr_t)p + bytes) / page * page;      // whole pages inside the buffer
+  static const bool huge = [] { const char* e = getenv("FQ_POPULATE_HUGE"); return !(e && e[0] == '0'); }();
+  if (huge && hi > lo) madvise((void*)lo, hi - lo, MADV_HUGEPAGE);       // where transparent huge pages are on request: 16 faults per 32 MiB instead of 8,192
   const size_t step = (size_t)4 << 20;
   for (; lo < hi; lo += step)
     if (madvise((void*)lo, hi - lo < step ? hi - lo : step, MADV_POPULATE_WRITE) != 0) return;
