@@ -586,3 +586,23 @@ def test_on_curve_device_op_is_bound(fq):
     d_in = device.DeviceBuffer.from_host(0, xy); d_out = device.DeviceBuffer(0, 2)
     device.dev_run("on_curve", 0, d_in, None, d_out, None, 2)
     assert list(d_out.to_host((2,))) == [1, 0]
+
+
+def test_sliced_pinned_arrays_and_rows_per_device(fq):
+    """pinned_empty(..., ndev=N) (fq_host_alloc_sliced: NUMA placement where the platform allows, always page-locked) and the report of
+    who processed what (fq_last_rows_per_device); with several GPUs the slices may be uneven (speed-proportional, work stealing) but
+    the bytes never change."""
+    from fourq_b200 import device
+    g = min(fq.device_count(), 8)
+    rng = np.random.default_rng(80)
+    n = 600_011
+    k = fq.pinned_empty((n, 32), ndev=max(g, 2)); k[:] = rng.integers(0, 256, (n, 32), np.uint8)
+    out = fq.pinned_empty((n, 32), ndev=max(g, 2))
+    ref = fq.MUL_base(np.array(k))
+    for ndev in sorted({1, g}):
+        for _ in range(3):                                   # later calls use the speeds measured by the earlier ones
+            out[:] = 0
+            fq.MUL_base(k, out=out, ndev=ndev)
+            assert (out == ref).all()
+            rows = device.last_rows_per_device(ndev)
+            assert sum(rows) == n and all(r > 0 for r in rows), rows

@@ -20,10 +20,13 @@ template <int NSLOT> struct SelectSlots {
     return S;
   }
 };
+#ifndef KEXP_THREADS
+#define KEXP_THREADS 128
+#endif
 #ifdef KEXP_MAXNREG
 #define KEXP_BOUNDS(MINB) __maxnreg__(KEXP_MAXNREG)
 #else
-#define KEXP_BOUNDS(MINB) __launch_bounds__(128, MINB)
+#define KEXP_BOUNDS(MINB) __launch_bounds__(KEXP_THREADS, MINB)
 #endif
 template <int MINB, int NSLOT> __global__ void KEXP_BOUNDS(MINB) k_main(const void* k, void* out, size_t n) {
   extern __shared__ uint4 smem[];
@@ -53,15 +56,15 @@ template <int MINB, int NSLOT> __global__ void KEXP_BOUNDS(MINB) k_main(const vo
 }
 
 template <int MINB, int NSLOT> void run(const char* name, const void* k, void* out, size_t n) {
-  int smem = NSLOT * 8 * 16 * 128;
+  int smem = NSLOT * 8 * 16 * KEXP_THREADS;
   cudaFuncSetAttribute(k_main<MINB, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_main<MINB, NSLOT>, 128, smem);
+  int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_main<MINB, NSLOT>, KEXP_THREADS, smem);
   cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_main<MINB, NSLOT>);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 1e9f;
   for (int it = 0; it < 4; it++) {
     cudaEventRecord(e0);
-    k_main<MINB, NSLOT><<<(unsigned)(n / 128), 128, smem>>>(k, out, n);
+    k_main<MINB, NSLOT><<<(unsigned)(n / KEXP_THREADS), KEXP_THREADS, smem>>>(k, out, n);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
   }
