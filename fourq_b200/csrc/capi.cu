@@ -172,11 +172,15 @@ struct CallWork {
     bool weighted = share != nullptr && ndev > 1 && n >= (size_t)ndev * 2 * full;
     for (int i = 0; weighted && i < ndev; i++) { if (share[i] > 0) total += share[i]; else weighted = false; }
     double f[64], fsum = 0;                                 // proportional to the measured speed, within +-25 % of the equal share
+    double spread = 0;
     for (int i = 0; weighted && i < ndev && i < 64; i++) {
       f[i] = share[i] / total * ndev;
+      if (f[i] - 1 > spread) spread = f[i] - 1;
+      if (1 - f[i] > spread) spread = 1 - f[i];
       f[i] = f[i] < 0.75 ? 0.75 : f[i] > 1.25 ? 1.25 : f[i];
       fsum += f[i];
     }
+    if (spread < 0.03) weighted = false;                   // GPUs within 3 % of each other: measurement noise, keep the slices equal
     size_t lo = 0;
     for (int i = 0; i < ndev; i++) {
       size_t len = per;
@@ -371,8 +375,10 @@ int ctx_init(DevCtx& c) {
   return FQ_OK;
 }
 
+thread_local bool tl_grew = false;       // a staging or scratch buffer was (re)allocated by this thread: the call's timing includes it
 int dbuf_reserve(Slot& s, int w, size_t bytes) {
   if (bytes <= s.dcap[w]) return FQ_OK;
+  tl_grew = true;
   if (s.dbuf[w]) CU(cudaFree(s.dbuf[w]));
   s.dbuf[w] = nullptr; s.dcap[w] = 0;
   CU(cudaMalloc(&s.dbuf[w], bytes));
@@ -381,6 +387,7 @@ int dbuf_reserve(Slot& s, int w, size_t bytes) {
 }
 int hbuf_reserve(Slot& s, int w, size_t bytes) {
   if (bytes <= s.hcap[w]) return FQ_OK;
+  tl_grew = true;
   if (s.hbuf[w]) CU(cudaFreeHost(s.hbuf[w]));
   s.hbuf[w] = nullptr; s.hcap[w] = 0;
   CU(cudaHostAlloc(&s.hbuf[w], bytes, cudaHostAllocPortable));
@@ -390,6 +397,7 @@ int hbuf_reserve(Slot& s, int w, size_t bytes) {
 int scratch_reserve(Slot& s, int op, size_t rows) {
   const size_t bytes = scratch_bytes(op, rows);
   if (bytes <= s.scratch_cap) return FQ_OK;
+  tl_grew = true;
   if (s.scratch) CU(cudaFree(s.scratch));
   s.scratch = nullptr; s.scratch_cap = 0;
   CU(cudaMalloc(&s.scratch, bytes));
@@ -461,6 +469,7 @@ struct SliceJob {
   uint8_t* out = nullptr; uint8_t* status = nullptr;
   CallWork* work = nullptr; int index = 0;                 // the call's rows and this GPU's slice number
   size_t rows_done = 0;
+  bool grew = false;                                       // buffers were allocated during this job: its speed is not representative
   bool pinned[kOperands] = {true, true, true, true, true};
   CallState* call = nullptr;
   // results
@@ -480,6 +489,7 @@ int feed_slice(DevCtx& c, SliceJob* j) {
   const OpDesc& d = j->d;
   int rc = FQ_OK;
   size_t r0 = 0, rows = 0;
+  tl_grew = false;
   for (int ci = 0; rc == FQ_OK && j->work->take(j->index, ci, &r0, &rows); ci++) {
     const int si = ci % slots_in_use();
     Slot& s = c.slot[si];
@@ -525,6 +535,7 @@ int feed_slice(DevCtx& c, SliceJob* j) {
     c.scv.notify_all();
   }
   if (rc != FQ_OK) job_fail(c, j, rc);
+  j->grew = tl_grew;
   { std::unique_lock<std::mutex> l(c.smu); c.scv.wait(l, [&] { return j->outstanding == 0; }); }
   return j->rc;
 }
@@ -643,7 +654,7 @@ int run_host(int op, const uint8_t* a, const uint8_t* b, const uint8_t* cbuf, ui
   if (rc_class >= 0 && ndev > 1)                       // remember how fast each GPU was (rows per ms of device time), for the next call's slices
     for (int i = 0; i < used; i++) {
       const SliceJob& j = jobs[(size_t)i];
-      if (j.rc != FQ_OK || j.kernel_ms <= 0.f || j.rows_done < 2 * dj.chunk_rows) continue;
+      if (j.rc != FQ_OK || j.grew || j.kernel_ms <= 0.f || j.rows_done < 2 * dj.chunk_rows) continue;
       std::atomic<double>& r = ctx_of(base + i).rate[rc_class];
       const double now = (double)j.rows_done / j.kernel_ms, old = r.load();
       r.store(old > 0 ? 0.5 * (old + now) : now);
