@@ -310,6 +310,12 @@ def measure_inproc(fq, world, algorithm, quick=False):
     same4 = bool((po1 == poN).all())
     res["cfg4"] = {"rows": n4, "ndev1_rows_per_s": n4 / t1, "ndevN_rows_per_s": n4 / tN, "ndev1_ms": t1 * 1e3, "ndevN_ms": tN * 1e3, "speedup": t1 / tN,
                    "ndevN_max_device_span_ms": kN, "ndevN_rows_per_device": rows4, "scaling": "strong", "parity_vs_ndev1": same4}
+    # what the box can move: the same 64 B of host traffic per row with next to no arithmetic (GFp2.neg), ndev = 1 and ndev = world
+    from fourq_b200 import _lib as L
+    tc1 = best(lambda: L.check(L.lib().fq_fp2_neg(L.ptr(pk), L.ptr(po1), n4, 1)))
+    tcN = best(lambda: L.check(L.lib().fq_fp2_neg(L.ptr(pk), L.ptr(po1), n4, world)))
+    res["copy_probe"] = {"rows": n4, "bytes_per_row": 64, "ndev1_ms": tc1 * 1e3, "ndevN_ms": tcN * 1e3, "ndev1_host_gbs": n4 * 64 / tc1 / 1e9, "ndevN_host_gbs": n4 * 64 / tcN / 1e9,
+                         "note": "fq_fp2_neg on the cfg 4 arrays: 32 B in + 32 B out per row and a trivial kernel -- the floor that host <-> device traffic puts under the cfg 4 call at the same ndev"}
     rows = (1 << (18 if quick else 20))
     n3 = rows * world
     k3 = fq.pinned_empty((n3, 32), ndev=world); k3[:] = np.random.default_rng(3).integers(0, 256, (n3, 32), np.uint8)

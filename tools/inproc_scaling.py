@@ -12,6 +12,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fourq_b200 as fq   # noqa: E402
+from fourq_b200 import _lib   # noqa: E402,F401
 
 
 def best(fn, reps=5):
@@ -26,7 +27,6 @@ def main():
     gpus = fq.device_count()
     ns = [g for g in (1, 2, 4, 8) if g <= gpus]
     sliced = os.environ.get("FQ_SLICED", "1") != "0"          # FQ_SLICED=0: ordinary page-locked arrays (for the A/B)
-    from fourq_b200 import _lib
     print(json.dumps({"gpu_numa_nodes": [int(_lib.lib().fq_device_numa_node(i)) for i in range(gpus)], "sliced_arrays": sliced}), flush=True)
     n4 = 1 << 24
     top = max(ns) if sliced else 1
@@ -39,6 +39,12 @@ def main():
         t1 = t1 or t
         print(json.dumps({"config": "cfg4 fixed-base keygen, 2^24 rows, strong scaling", "ndev": g, "ms": t * 1e3, "rows_per_s": n4 / t, "speedup_vs_ndev1": t1 / t,
                           "device_span_ms": fq.last_kernel_ms(), "rows_per_device": fq.device.last_rows_per_device(g), "parity_vs_ndev1": bool((o == ref).all())}), flush=True)
+    # the same 64 B of host traffic per row with next to no arithmetic: GFp2.neg on 2^24 rows -- what the box can move
+    pn = fq.pinned_empty((n4, 32), ndev=top)
+    for g in ns:
+        t = best(lambda: _lib.check(_lib.lib().fq_fp2_neg(_lib.ptr(pk), _lib.ptr(pn), n4, g)))
+        print(json.dumps({"config": "copy-bound probe: GFp2.neg, 2^24 rows, 32 B in + 32 B out per row", "ndev": g, "ms": t * 1e3, "rows_per_s": n4 / t,
+                          "host_traffic_gbs": n4 * 64 / t / 1e9}), flush=True)
     rows = 1 << 20
     e1 = None
     for g in ns:
