@@ -69,6 +69,16 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"(import|from|CDLL|dlopen)[^\n]*hostsim", src), f
 
 
+def test_tools_do_not_use_the_oracle():
+    """Only tests/ (incl. tests/checks), smoke() and bench.py's checking legs may touch oracle/: the measurement tools must not."""
+    tools = os.path.join(ROOT, "tools")
+    for dirpath, _, files in os.walk(tools):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle|from oracle|import oracle|c_oracle|fourq_oracle", src, re.M), f
+
+
 def test_c_example_compiles_links_and_fails_loudly_without_a_gpu(libpath, tmp_path):
     """examples/dh_example.c binds the C ABI from plain C; without a CUDA device it must exit with the no-device error."""
     import shutil
