@@ -4,7 +4,7 @@
 // Table residency.  T[i] = [2i+1]P in R2 is 8 x 4 x 32 B = 1 KiB per thread.  Entries 0..6 live in shared memory as
 // 128-bit words laid out [entry][quad][thread] (consecutive threads -> consecutive 16 B: conflict-free LDS.128/STS.128),
 // entry 7 stays in registers: 7 x 128 B x 128 threads = 112 KiB per CTA, two CTAs per SM.
-// Selection issues the loads of ALL entries and keeps one by predicate (tab_select); the sign is applied with masks.
+// Selection issues the loads of ALL entries and keeps one (tab_select: strict scan by default); the sign is applied with masks.
 #pragma once
 #include "codec.cuh"
 #include "scalar.cuh"
@@ -28,15 +28,16 @@ FQ_FN ptR2 tab_load(const TabView& T, int e) {
 
 // Constant-time table selection.  Every thread issues the loads of ALL entries in the same order from addresses that do not
 // depend on the digit; the digit only decides what each load keeps.  Two variants, compiled side by side and chosen per
-// launch (template parameter STRICT; fq_set_select_mode / FQ_STRICT_SELECT=1 at run time):
-//   masked loads (library default)  `@p ld.shared.v4` -- a lane whose predicate is off transfers nothing and keeps its
-//                            registers, so the select costs no ALU instruction at all (56 LDS.128 per select).  The number of
-//                            shared-memory wavefronts of a load then depends on which lanes are on: a batch in which all 32
-//                            rows of every warp pick the same entry runs the ladder 0.4 % faster than one in which they differ
-//                            (tools/ct_timing.py, profiles/r01_ct_timing.jsonl).
-//   strict scan              every lane loads every entry and each word goes through one SEL per entry (56 LDS.128 + 224
-//                            SEL): no data-dependent memory activity of any kind, no measurable timing difference; the
-//                            ladder is 1-3 % slower, the fixed-base comb kernel (short iterations) 8 %.
+// launch (template parameter STRICT; fq_set_select_mode / FQ_STRICT_SELECT at run time):
+//   strict scan (library default)   every lane loads every entry and each word goes through one SEL per entry (56 LDS.128 + 224
+//                            SEL): no data-dependent memory activity of any kind; ladder time flat to 0.05 % over scalar
+//                            distributions (profiles/r02_ct_timing.jsonl).  This is what draft-ladd-cfrg-4q.md:653-656, :753-755 ask for.
+//   masked loads (opt-in)    `@p ld.shared.v4` -- a lane whose predicate is off transfers nothing and keeps its registers, so
+//                            the select costs no ALU instruction at all (56 LDS.128 per select): the ladder is 1 % faster, the
+//                            fixed-base comb kernel (short iterations) 8 %.  The number of shared-memory wavefronts of a load then
+//                            depends on which lanes are on: a batch in which all 32 rows of every warp pick the same entry runs the
+//                            ladder 0.4 % faster than one in which they differ (profiles/r01_ct_timing.jsonl).  For non-secret
+//                            scalars only.
 // No secret-dependent branch or address in either; the layout [entry][quad][thread] keeps lane L on banks 4L..4L+3 for
 // every entry, so there is no digit-dependent bank conflict.  (The template default below only concerns code that does not
 // pass STRICT explicitly: the CPU simulation and the experiments in tools/kexp.)
