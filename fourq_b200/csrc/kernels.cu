@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_encode(const void* xy, void* enc, size_
 
 // fixed base, the reference's shape: [k]G (DH = false) or [k][392]G (DH = true) by MUL_windowed / MUL_endo on the base point's
 // table.  The CTA copies the 1 KiB table from the constant bank into shared memory once; the selection then reads it by
-// broadcast (dh.cuh SelectBroadcast).  The result stays projective: k_dh_finish (kernels_dh.cuh) normalises four rows per
+// broadcast (dh.cuh SelectBroadcast).  The result stays projective: k_dh_finish (kernels_dh.cuh) normalises sixteen rows per
 // inversion, rejects the neutral point for DH, and encodes.
 template <bool DH, bool ENDO, bool STRICT> __global__ void __launch_bounds__(256)
 k_fixed_base(const void* __restrict__ k, DhScratch sc, size_t n) {

@@ -1,7 +1,7 @@
 // kernels_comb.cu -- fixed-base kernels on per-digit tables (comb.cuh): fq_mul_base_comb, fq_dh_base_comb.
 // One thread = one row; the 47.25 KiB table of the base point is copied once per CTA from global to shared memory and
 // then read with warp-uniform addresses (broadcast), so the per-thread state is registers only.  k_comb leaves the result
-// projective; k_dh_finish (kernels_dh.cuh) normalises four rows per inversion and encodes.
+// projective; k_dh_finish (kernels_dh.cuh) normalises sixteen rows per inversion and encodes.
 #include "kernels_dh.cuh"
 #include "comb.cuh"
 

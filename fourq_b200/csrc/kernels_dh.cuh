@@ -7,7 +7,7 @@
 //                The table goes to a scratch buffer in HBM laid out [entry][quad][row] (1 KiB per row, coalesced).
 //   k_dh_ladder  copies the row's table into shared memory ([entry][quad][thread], 112 KiB per CTA, entry 7 in
 //                registers) and runs the 64 x (DBL + ADD) or 62 x (4 DBL + ADD) loop; two CTAs per SM (shared memory
-//                and ~200 registers both allow 256 threads).  Writes (X, Y, Z) to scratch.
+//                and the 248 registers of the strict-scan loop both allow 256 threads).  Writes (X, Y, Z) to scratch.
 //   k_dh_finish  each thread normalises FQ_BATCHINV_ROWS rows with ONE inversion (Montgomery's trick: prefix products parked
 //                in the output rows, one x^(p-2) chain, back-substitution), checks for the neutral point, encodes, writes
 //                result and status (batchinv.cuh).
