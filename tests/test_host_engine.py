@@ -199,6 +199,19 @@ def test_a_slow_gpu_gets_help_from_the_others(eng, sim):
     assert eng.mock_violations() == 0
 
 
+def test_tiny_and_ragged_batches_on_every_gpu_count(eng, sim):
+    """Fewer rows than GPUs, one row, sizes around the 128-row granularity: the empty slices get no job and every row is done once."""
+    rng = np.random.default_rng(14)
+    for n in (1, 2, 3, 4, 5, 127, 129, 1000):
+        for ndev in (1, 2, 3, 4):
+            a = rng.integers(0, 256, (n, 32), np.uint8); out = np.zeros_like(a); ref = np.zeros_like(a)
+            assert eng.fq_fp2_neg(P(a), P(out), n, ndev) == 0, eng.fq_last_error()
+            sim.sim_fp2_op(5, P(a), None, P(ref), ctypes.c_size_t(n))
+            assert (out == ref).all(), (n, ndev)
+            rows = (ctypes.c_size_t * ndev)()
+            assert eng.fq_last_rows_per_device(rows, ndev) == 0 and sum(rows) == n
+
+
 def test_argument_errors(eng):
     a = np.zeros((4, 32), np.uint8); out = np.zeros_like(a)
     assert eng.fq_fp2_sqr(P(a), P(out), 4, 0) == _lib.FQ_ERR_ARG
