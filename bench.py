@@ -446,7 +446,10 @@ def main():
         fq.trim()
         barrier()
         if rank == 0:
-            inproc = measure_inproc(fq, world, args.algorithm, quick=args.quick)
+            try:
+                inproc = measure_inproc(fq, world, args.algorithm, quick=args.quick)
+            except Exception as e:                       # a parity failure is a SystemExit and still aborts the run; anything else must not cost the headline line
+                inproc = {"error": "%s: %s" % (type(e).__name__, e)}
             fq.set_device(local_rank)
         dist.barrier(group=cpu_group)
 
@@ -512,7 +515,12 @@ def main():
             parity["checker_rows_per_s"] = m / parity["seconds"]      # the C port on all host cores (threads), for scale
         configs = None
         if not args.no_configs and rows == ROWS_PER_GPU and world == 1:      # N > 1 runs carry `inproc` instead
-            configs = measure_configs(fq, fqdev, local_rank, wide_peak, hbm, sum(kernel_ms) / len(kernel_ms), args.algorithm, quick=args.quick)
+            try:
+                configs = measure_configs(fq, fqdev, local_rank, wide_peak, hbm, sum(kernel_ms) / len(kernel_ms), args.algorithm, quick=args.quick)
+            except AssertionError:
+                raise SystemExit("PARITY FAILURE: a configs batch differs from the oracle")
+            except Exception as e:
+                configs = {"error": "%s: %s" % (type(e).__name__, e)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",

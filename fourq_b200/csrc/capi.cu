@@ -158,13 +158,15 @@ struct CallWork {
   std::mutex mu;
   struct Range { size_t lo, hi; bool ramp; };
   std::vector<Range> r;               // rows of each slice not yet handed out
-  size_t full = 0, small = 0;
+  size_t full = 0, small = 0, quant = 128;
   bool steal = true, abort = false;
   // share: optional relative speeds of the GPUs (rows per ms of their last calls); null or incomplete -> equal slices
   void init(size_t n, int ndev, size_t full_rows, const double* share = nullptr) {
     full = full_rows;
     small = full / 8 >= 16384 ? full / 8 : 16384;
     if (small > full) small = full;
+    static const size_t q_env = [] { const char* e = getenv("FQ_CHUNK_QUANT"); long long x = e ? atoll(e) : 0; return x >= 128 ? (size_t)x / 128 * 128 : (size_t)128; }();
+    quant = q_env <= small ? q_env : 128;
     static const bool steal_on = [] { const char* e = getenv("FQ_STEAL"); return !(e && e[0] == '0'); }();
     steal = steal_on;
     const size_t per = (n + (size_t)ndev - 1) / (size_t)ndev;
@@ -203,8 +205,8 @@ struct CallWork {
       size_t sz = full;
       if (own.ramp) { sz = small; for (int t = 0; t < taken && sz < full; t++) sz = sz * 2 < full ? sz * 2 : full; }
       size_t n = sz < left ? sz : left;
-      if (own.ramp && left > small && left <= 2 * n) {              // ramp down by halves, in units of 128 rows
-        n = (left / 2 + 127) / 128 * 128;
+      if (own.ramp && left > small && left <= 2 * n) {              // ramp down by halves, in units of `quant` rows
+        n = (left / 2 + quant - 1) / quant * quant;
         if (n > full) n = full;
         if (n > left) n = left;
       }
