@@ -179,7 +179,8 @@ FQ_FN void endo_next_digit(scal& s, u32& idx, u32& neg) {
 // curve4q.py:385-403: T[0] = P, T[1] = P+Q, T[2] = P+R, T[3] = P+Q+R, T[4+i] = T[i] + S with Q = phi(P), R = psi(P),
 // S = psi(phi(P)); entries in R2, 0..6 to shared memory, returns T[7].
 FQ_FN ptR2 endo_tab_build(const TabView& T, const ptR1& P) {
-  ptR1 Qp = endo_phi(P);
+  const pt3 tP = endo_tau(pt3_of(P));        // tau(P) is the first step of both phi(P) and psi(P) (curve4q.py:318-322): evaluated once
+  ptR1 Qp = endo_tau_dual(endo_upsilon(tP)); // phi(P)
   ptR3 A3;                                   // the left operand of each addition, in R3
   ptR2 T0, Ti;
   ptR1 S;
@@ -187,7 +188,7 @@ FQ_FN ptR2 endo_tab_build(const TabView& T, const ptR1& P) {
   tab_store(T, 0, T0);
   pt_r1_to_r3_c(&A3, &Qp);
   pt_add_core_c(&S, &A3, &T0); pt_r1_to_r2_c(&Ti, &S); tab_store(T, 1, Ti);          // T[1] = Q + P
-  S = endo_psi(P);
+  S = endo_tau_dual(endo_chi(tP));           // psi(P)
   pt_r1_to_r3_c(&A3, &S);
   pt_add_core_c(&S, &A3, &Ti); pt_r1_to_r2_c(&Ti, &S); tab_store(T, 3, Ti);          // T[3] = R + T[1]
   pt_add_core_c(&S, &A3, &T0); pt_r1_to_r2_c(&Ti, &S); tab_store(T, 2, Ti);          // T[2] = R + P
