@@ -57,40 +57,7 @@ def model_imads(r):
     return int(48 * r["M"] + 32 * r["S"] + 16 * g["M"] + 10 * g["S"] + inv)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", type=int, default=1 << 20)
-    ap.add_argument("--opmix", default=None, help="JSON written by tools/ncu_kernels_opmix.py: executed IMAD.WIDE per row of every kernel")
-    ap.add_argument("--launch-only", action="store_true", help="launch every variant once (for an ncu capture) and print nothing")
-    args = ap.parse_args()
-    n = args.rows
-    rng = np.random.default_rng(17)
-    k = rng.integers(0, 256, (n, 32), np.uint8)
-    u = rng.integers(0, 256, (n, 32), np.uint8)
-    # the base point G as an affine row x0 | x1 | y0 | y1 (curve4q.py:19-20; its y half is the encoding 87b2cb2b... of curve4q.py:478)
-    G = np.frombuffer(bytes.fromhex("aa33387bad92652805b32f7c2372341af677ac60b39f86969caa78283f551f1e"
-                                    "87b2cb2b46a224b95a7820a19bee3f0e5c8b4c8444c3a74942020e63f84a1c6e"), np.uint8)
-    xy = np.tile(G, (n, 1))                                   # compare.py multiplies the base point (compare.py:172, :189)
-    dk = fqdev.DeviceBuffer.from_host(0, k); du = fqdev.DeviceBuffer.from_host(0, u); dxy = fqdev.DeviceBuffer.from_host(0, xy)
-    dout = fqdev.DeviceBuffer(0, n * 64); dst = fqdev.DeviceBuffer(0, n)
-    inputs = {"dh_affine": dxy, "dh_endo_affine": dxy, "x25519": du}
-    if args.launch_only:
-        for _, _, op, _ in VARIANTS:
-            fqdev.dev_run(op, 0, dk, inputs.get(op), dout, dst, n)
-        return
-    opmix = json.load(open(args.opmix)) if args.opmix else None
-    print("fourq_b200 compare (batched impl/compare.py), %d rows per batch, table selection: %s" % (n, "strict scan" if fq.get_select_mode() else "masked loads"))
-    print()
-    # ---- 1. field operations (compare.py:14-49)
-    print("===== Time for %d field operations (GF(p^2) rows, kernel time, device-resident) =====" % n)
-    print()
-    print("%-5s %10s %14s" % ("Op", "GFp2", "ops/s"))
-    a = fqdev.DeviceBuffer.from_host(0, rng.integers(0, 256, (n, 32), np.uint8)); b = fqdev.DeviceBuffer.from_host(0, rng.integers(0, 256, (n, 32), np.uint8))
-    for name in ("add", "mul", "sqr", "inv"):
-        ms = best_ms("fp2_" + name, a, b if name in ("add", "mul") else None, dout, None, n)
-        print("%-5s %8.4fms %14.4g" % (name, ms, n / ms * 1e3))
-    print("(GF(2^255-19) field operations are not exposed: X25519 is a parity/throughput comparison kernel only)")
-    print()
+def print_counts(opmix):
     # ---- 2. operation counts (compare.py:51-169)
     counts = json.load(open(os.path.join(ROOT, "tests", "golden", "opcounts.json")))
     print("===== Field operation count (the reference's counters; tests/golden/opcounts.json) =====")
@@ -101,7 +68,7 @@ def main():
         for key, _, _, kernels in VARIANTS:
             tot = 0.0
             for pat in kernels:
-                hits = [v for name, v in opmix.items() if pat in name]
+                hits = [v for name, v in opmix.items() if pat in name.replace("(bool)", "")]
                 if not hits:
                     tot = None; break
                 tot += hits[0]["wide_per_row"]
@@ -118,6 +85,47 @@ def main():
     print("executed WIDE = IMAD.WIDE.U32[.X] instructions per row summed over the variant's kernels (ncu SourceCounters); it is lower")
     print("than the model where the kernels skip multiplications by 2 and 1/2, use a dedicated GF(p) squaring, and share one inversion per 16 rows.")
     print()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=1 << 20)
+    ap.add_argument("--opmix", default=None, help="JSON written by tools/ncu_kernels_opmix.py: executed IMAD.WIDE per row of every kernel")
+    ap.add_argument("--launch-only", action="store_true", help="launch every variant once (for an ncu capture) and print nothing")
+    ap.add_argument("--counts-only", action="store_true", help="print the operation-count table only (needs no GPU)")
+    args = ap.parse_args()
+    n = args.rows
+    opmix = json.load(open(args.opmix)) if args.opmix else None
+    if args.counts_only:
+        print_counts(opmix)
+        return
+    rng = np.random.default_rng(17)
+    k = rng.integers(0, 256, (n, 32), np.uint8)
+    u = rng.integers(0, 256, (n, 32), np.uint8)
+    # the base point G as an affine row x0 | x1 | y0 | y1 (curve4q.py:19-20; its y half is the encoding 87b2cb2b... of curve4q.py:478)
+    G = np.frombuffer(bytes.fromhex("aa33387bad92652805b32f7c2372341af677ac60b39f86969caa78283f551f1e"
+                                    "87b2cb2b46a224b95a7820a19bee3f0e5c8b4c8444c3a74942020e63f84a1c6e"), np.uint8)
+    xy = np.tile(G, (n, 1))                                   # compare.py multiplies the base point (compare.py:172, :189)
+    dk = fqdev.DeviceBuffer.from_host(0, k); du = fqdev.DeviceBuffer.from_host(0, u); dxy = fqdev.DeviceBuffer.from_host(0, xy)
+    dout = fqdev.DeviceBuffer(0, n * 64); dst = fqdev.DeviceBuffer(0, n)
+    inputs = {"dh_affine": dxy, "dh_endo_affine": dxy, "x25519": du}
+    if args.launch_only:
+        for _, _, op, _ in VARIANTS:
+            fqdev.dev_run(op, 0, dk, inputs.get(op), dout, dst, n)
+        return
+    print("fourq_b200 compare (batched impl/compare.py), %d rows per batch, table selection: %s" % (n, "strict scan" if fq.get_select_mode() else "masked loads"))
+    print()
+    # ---- 1. field operations (compare.py:14-49)
+    print("===== Time for %d field operations (GF(p^2) rows, kernel time, device-resident) =====" % n)
+    print()
+    print("%-5s %10s %14s" % ("Op", "GFp2", "ops/s"))
+    a = fqdev.DeviceBuffer.from_host(0, rng.integers(0, 256, (n, 32), np.uint8)); b = fqdev.DeviceBuffer.from_host(0, rng.integers(0, 256, (n, 32), np.uint8))
+    for name in ("add", "mul", "sqr", "inv"):
+        ms = best_ms("fp2_" + name, a, b if name in ("add", "mul") else None, dout, None, n)
+        print("%-5s %8.4fms %14.4g" % (name, ms, n / ms * 1e3))
+    print("(GF(2^255-19) field operations are not exposed: X25519 is a parity/throughput comparison kernel only)")
+    print()
+    print_counts(opmix)
     # ---- 3. DH timing (compare.py:171-219)
     print("===== Time for %d Diffie-Hellman operations =====" % n)
     print()
