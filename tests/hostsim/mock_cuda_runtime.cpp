@@ -248,6 +248,18 @@ __attribute__((visibility("default"))) long mock_live_allocs(int type, long* byt
   if (bytes) *bytes = b;
   return n;
 }
+// number of live allocations of `type` (2 = device, 1 = pinned host) of at least `min_bytes` bytes that hold a non-zero byte
+__attribute__((visibility("default"))) long mock_nonzero_allocs(int type, long min_bytes) {
+  sync_all();
+  std::lock_guard<std::mutex> l(G().mu);
+  long n = 0;
+  for (auto& kv : G().allocs) {
+    if ((int)kv.second.type != type || (long)kv.second.bytes < min_bytes) continue;
+    const unsigned char* q = (const unsigned char*)kv.first;
+    for (size_t i = 0; i < kv.second.bytes; i++) if (q[i]) { n++; break; }
+  }
+  return n;
+}
 // while on, freeing a device or pinned buffer that is not all zeros counts as a violation (fq_trim's wipe)
 __attribute__((visibility("default"))) void mock_expect_zero_on_free(int on) { G().expect_zero_free.store(on); }
 __attribute__((visibility("default"))) int mock_is_pinned(const void* p) {

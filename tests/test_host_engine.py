@@ -284,6 +284,31 @@ def test_trim_wipes_and_frees_everything(eng):
     assert eng.mock_live_allocs(2, ctypes.byref(nb)) <= 4                  # only the per-device comb tables stay
 
 
+def test_wipe_after_call_leaves_no_secret_in_the_engine_buffers():
+    """FQ_WIPE_AFTER_CALL=1 (read once per process, hence a child process): after a keygen call every staging and scratch buffer the
+    engine keeps -- device and pinned -- is all zeros; the caller's own arrays are untouched."""
+    so = os.path.join(SIM_DIR, "libfq_mockengine.so")
+    code = """
+import ctypes, sys, numpy as np
+sys.path.insert(0, %r)
+from fourq_b200 import _lib
+L = _lib.bind(ctypes.CDLL(%r))
+L.mock_nonzero_allocs.restype = ctypes.c_long; L.mock_nonzero_allocs.argtypes = [ctypes.c_int, ctypes.c_long]
+L.mock_set_device_count(2)
+k = np.random.default_rng(1).integers(1, 256, (700, 32), np.uint8); out = np.zeros_like(k); st = np.zeros(700, np.uint8)
+assert L.fq_dh_base_comb(_lib.ptr(k), _lib.ptr(out), _lib.ptr(st), 700, 2) == 0
+assert out.any() and k.any()
+print(L.mock_nonzero_allocs(2, 1024), L.mock_nonzero_allocs(1, 1024))
+""" % (os.path.join(HERE, ".."), so)
+    res = {}
+    for wipe in ("0", "1"):
+        r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, FQ_WIPE_AFTER_CALL=wipe))
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[wipe] = [int(x) for x in r.stdout.split()]
+    assert res["0"][0] > 0 and res["0"][1] > 0           # without the switch the scalars and results stay in the staging buffers
+    assert res["1"] == [0, 0]                            # with it nothing of at least 1 KiB that the engine allocated holds data
+
+
 @pytest.mark.parametrize("san", ["tsan", "asan"])
 def test_engine_stress_under_sanitizers(san):
     """ThreadSanitizer / AddressSanitizer + UBSan over the engine's threads, staging and scratch sizing (engine_stress.cpp)."""
