@@ -15,7 +15,8 @@ FPOP = {"mul": 0, "sqr": 1, "inv": 2, "add": 3, "sub": 4, "neg": 5, "invsqrt": 6
 DEVOP = {"fp_mul": 32, "fp_sqr": 33, "fp_inv": 34, "fp_add": 35, "fp_sub": 36, "fp_neg": 37, "fp_invsqrt": 38,
          "fp2_mul": 0, "fp2_sqr": 1, "fp2_inv": 2, "fp2_add": 3, "fp2_sub": 4, "fp2_neg": 5, "fp2_conj": 6, "fp2_invsqrt": 7, "fp2_select": 8, "fp_select": 9,
          "decode": 16, "decode_spec": 29, "encode": 17, "dh": 18, "dh_affine": 19, "dh_base": 20, "mul_base": 21, "x25519": 22,
-         "dh_endo": 23, "dh_endo_affine": 24, "dh_endo_base": 25, "mul_endo_base": 26, "dh_base_comb": 27, "mul_base_comb": 28, "on_curve": 30}
+         "dh_endo": 23, "dh_endo_affine": 24, "dh_endo_base": 25, "mul_endo_base": 26, "dh_base_comb": 27, "mul_base_comb": 28, "on_curve": 30,
+         "f25519_mul": 48, "f25519_sqr": 49, "f25519_inv": 50, "f25519_add": 51, "f25519_sub": 52}
 
 
 class FourQError(RuntimeError):
@@ -49,6 +50,7 @@ def bind(L):
         "fq_fp2_conj": ([vp, vp, sz, i], i), "fq_fp2_invsqrt": ([vp, vp, sz, i], i),
         "fq_fp_select": ([vp, vp, vp, vp, sz, i], i), "fq_fp2_select": ([vp, vp, vp, vp, sz, i], i),
         "fq_fp_op": ([i, vp, vp, vp, sz, i], i),
+        "fq_fp25519_op": ([i, vp, vp, vp, sz, i], i),
         "fq_decode": ([vp, vp, vp, sz, i], i), "fq_decode_spec": ([vp, vp, vp, sz, i], i), "fq_encode": ([vp, vp, sz, i], i), "fq_point_on_curve": ([vp, vp, sz, i], i),
         "fq_dh": ([vp, vp, vp, vp, sz, i], i), "fq_dh_affine": ([vp, vp, vp, vp, sz, i], i),
         "fq_dh_base": ([vp, vp, vp, sz, i], i), "fq_mul_base": ([vp, vp, sz, i], i),
@@ -72,7 +74,7 @@ def bind(L):
 
 
 EXPORTS = ["fq_version", "fq_device_count", "fq_last_error", "fq_set_device_base", "fq_set_select_mode", "fq_get_select_mode", "fq_trim", "fq_last_kernel_ms", "fq_last_rows_per_device", "fq_fp2_mul",
-           "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_fp2_invsqrt", "fq_fp_select", "fq_fp2_select", "fq_fp_op", "fq_decode", "fq_decode_spec", "fq_encode", "fq_point_on_curve",
+           "fq_fp2_sqr", "fq_fp2_inv", "fq_fp2_add", "fq_fp2_sub", "fq_fp2_neg", "fq_fp2_conj", "fq_fp2_invsqrt", "fq_fp_select", "fq_fp2_select", "fq_fp_op", "fq_fp25519_op", "fq_decode", "fq_decode_spec", "fq_encode", "fq_point_on_curve",
            "fq_dh", "fq_dh_affine", "fq_dh_base", "fq_mul_base", "fq_dh_endo", "fq_dh_endo_affine", "fq_dh_endo_base",
            "fq_mul_endo_base", "fq_dh_base_comb", "fq_mul_base_comb", "fq_x25519", "fq_host_alloc", "fq_host_free", "fq_host_alloc_sliced", "fq_device_numa_node",
            "fq_dev_alloc", "fq_dev_free", "fq_dev_upload", "fq_dev_download", "fq_dev_run", "fq_dev_run3", "fq_dev_last_phase_ms", "fq_dev_flush_l2", "fq_imad_peak"]

@@ -107,6 +107,9 @@ OpDesc describe(int op) {
     case FQ_DEVOP_DH_BASE_COMB: return {op, {32, 0, 0}, 32, true, (size_t)148 * 2 * 256 * 4};
     case FQ_DEVOP_MUL_BASE_COMB: return {op, {32, 0, 0}, 32, false, (size_t)148 * 2 * 256 * 4};
     case FQ_DEVOP_X25519: return {op, {32, 32, 0}, 32, false, M / 8};
+    case FQ_DEVOP_F25519_BASE + FQ_FP_MUL: case FQ_DEVOP_F25519_BASE + FQ_FP_ADD: case FQ_DEVOP_F25519_BASE + FQ_FP_SUB: return {op, {32, 32, 0}, 32, false, M};
+    case FQ_DEVOP_F25519_BASE + FQ_FP_SQR: return {op, {32, 0, 0}, 32, false, M};
+    case FQ_DEVOP_F25519_BASE + FQ_FP_INV: return {op, {32, 0, 0}, 32, false, M / 4};
     default: return {-1, {0, 0, 0}, 0, false, 0};
   }
 }
@@ -464,6 +467,9 @@ cudaError_t launch(const DevCtx& cx, int op, const void* a, const void* b, const
     case FQ_DEVOP_DH_ENDO_BASE: return fqk_fixed_base(1, 1, strict, a, out, status, n, scratch, s);
     case FQ_DEVOP_MUL_ENDO_BASE: return fqk_fixed_base(0, 1, strict, a, out, nullptr, n, scratch, s);
     case FQ_DEVOP_X25519: return fqk_x25519(a, b, out, n, scratch, s);
+    case FQ_DEVOP_F25519_BASE + FQ_FP_MUL: case FQ_DEVOP_F25519_BASE + FQ_FP_SQR: case FQ_DEVOP_F25519_BASE + FQ_FP_INV:
+    case FQ_DEVOP_F25519_BASE + FQ_FP_ADD: case FQ_DEVOP_F25519_BASE + FQ_FP_SUB:
+      return fqk_f25_op(op - FQ_DEVOP_F25519_BASE, a, b, out, n, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -796,6 +802,10 @@ int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n,
   if (op < FQ_FP_MUL || op > FQ_FP_INVSQRT) return fail(FQ_ERR_ARG, "unknown GF(p) operation %d", op);
   return run_host(FQ_DEVOP_FP_BASE + op, a, b, nullptr, out, nullptr, n, ndev);
 }
+int fq_fp25519_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev) {
+  if (op < FQ_FP_MUL || op > FQ_FP_SUB) return fail(FQ_ERR_ARG, "unknown GF(2^255-19) operation %d", op);
+  return run_host(FQ_DEVOP_F25519_BASE + op, a, b, nullptr, out, nullptr, n, ndev);
+}
 int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE, enc, nullptr, nullptr, xy, status, n, ndev); }
 int fq_point_on_curve(const uint8_t* xy, uint8_t* ok, size_t n, int ndev) { return run_host(FQ_DEVOP_ON_CURVE, xy, nullptr, nullptr, ok, nullptr, n, ndev); }
 int fq_decode_spec(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev) { return run_host(FQ_DEVOP_DECODE_SPEC, enc, nullptr, nullptr, xy, status, n, ndev); }
@@ -892,7 +902,7 @@ int fq_dev_run3(int op, int dev, const void* a, const void* b, const void* c, vo
   DevLock L(dev); if (L.rc != FQ_OK) return L.rc;
   const OpDesc d = describe(op);
   if (d.op < 0 || iters < 1) return fail(FQ_ERR_ARG, "bad op/iters");
-  if ((op == FQ_DEVOP_FP2_INV) && a == out) return fail(FQ_ERR_ARG, "fp2_inv: out must not alias a (the prefix products are parked in out)");
+  if ((op == FQ_DEVOP_FP2_INV || op == FQ_DEVOP_F25519_BASE + FQ_FP_INV) && a == out) return fail(FQ_ERR_ARG, "inv: out must not alias a (the prefix products are parked in out)");
   DevCtx& cx = *L.c;
   Slot& s = cx.slot[0];
   const bool dh = is_dh_op(op);

@@ -35,4 +35,5 @@ size_t fqk_comb_scratch_bytes(size_t n);     // device scratch the caller passes
 cudaError_t fqk_comb(int dh, int strict, const void* tabs, const void* k, void* out, void* status, size_t n, void* scratch, int sms, cudaStream_t s);
 size_t fqk_x25519_scratch_bytes(size_t n);     // device scratch the caller passes to fqk_x25519 (x2, z2 of every row)
 cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, void* scratch, cudaStream_t s);
+cudaError_t fqk_f25_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s);   // GF(2^255-19), 32-byte rows, op = FQ_FP_MUL.._SUB of the header
 cudaError_t fqk_imad_peak(int variant, void* scratch, int blocks, int trips, cudaStream_t s);

@@ -35,3 +35,37 @@ cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, void* 
   k_x25519_finish<<<(unsigned)((groups + 63) / 64), 64, 0, s>>>((const uint4*)scratch, npad, out, n);
   return cudaGetLastError();
 }
+
+// GFp25519 field ops (fields.py:267-362), one thread = one 32-byte row; inv shares one chain between FQ_BATCHINV_ROWS rows
+template <int OP> __global__ void __launch_bounds__(256) k_f25_op(const void* a, const void* b, void* out, size_t n) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  u32 wa[8], wb[8], wo[8];
+  ld8(a, row, wa);
+  if (OP == FQ_F25OP_MUL || OP == FQ_F25OP_ADD || OP == FQ_F25OP_SUB) ld8(b, row, wb);
+  row_f25_op<OP>(wa, wb, wo);
+  st8(out, row, wo);
+}
+__global__ void __launch_bounds__(64) k_f25_inv_batched(const void* __restrict__ a, void* __restrict__ out, size_t n) {
+  F25InvIO io;
+  io.a = reinterpret_cast<const uint4*>(a); io.out = reinterpret_cast<uint4*>(out); io.n = n;
+  io.stride = (size_t)gridDim.x * blockDim.x; io.t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  batch_invert<F25Ops>(io, FQ_BATCHINV_ROWS);
+}
+cudaError_t fqk_f25_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const unsigned g = (unsigned)((n + 255) / 256);
+  switch (op) {
+    case FQ_F25OP_MUL: k_f25_op<FQ_F25OP_MUL><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQ_F25OP_SQR: k_f25_op<FQ_F25OP_SQR><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQ_F25OP_ADD: k_f25_op<FQ_F25OP_ADD><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQ_F25OP_SUB: k_f25_op<FQ_F25OP_SUB><<<g, 256, 0, s>>>(a, b, out, n); break;
+    case FQ_F25OP_INV: {
+      const size_t groups = (n + FQ_BATCHINV_ROWS - 1) / FQ_BATCHINV_ROWS;
+      k_f25_inv_batched<<<(unsigned)((groups + 63) / 64), 64, 0, s>>>(a, out, n);
+      break;
+    }
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}

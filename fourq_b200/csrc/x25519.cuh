@@ -279,20 +279,24 @@ struct F25Ops {
   static FQ_MFN f25 mul(const f25& a, const f25& b) { return f25_mul(a, b); }
   static FQ_MFN f25 inv(const f25& a) { return f25_inv(a); }
 };
+// a loose value that is 0 mod p (0, p or 2p) is replaced by one; zero = all ones if it was
+FQ_FN f25 f25_one_if_zero(f25 v, u32& zero) {
+  f25 c = f25_canon(v);
+  u32 nz = 0;
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) nz |= c.v[i];
+  zero = nz == 0 ? 0xffffffffu : 0u;
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) v.v[i] = (v.v[i] & ~zero) | ((i == 0 ? 1u : 0u) & zero);
+  return v;
+}
 struct X25519FinIO {
   const uint4* scratch; size_t npad; uint4* out; size_t n, t, stride;
   FQ_MFN f25 z(int j, u32& zero) const {
     const size_t row = t + (size_t)j * stride;
     f25 v = f25_small(1);
     if (row < n) v = ld_f25(scratch + 2 * npad + row, npad);
-    f25 c = f25_canon(v);
-    u32 nz = 0;
-FQ_UNROLL
-    for (int i = 0; i < 8; i++) nz |= c.v[i];
-    zero = nz == 0 ? 0xffffffffu : 0u;
-FQ_UNROLL
-    for (int i = 0; i < 8; i++) v.v[i] = (v.v[i] & ~zero) | ((i == 0 ? 1u : 0u) & zero);
-    return v;
+    return f25_one_if_zero(v, zero);
   }
   FQ_MFN void park(int j, const f25& acc) const {
     const size_t row = t + (size_t)j * stride;
@@ -306,6 +310,49 @@ FQ_UNROLL
     const size_t row = t + (size_t)j * stride;
     if (row >= n) return;
     f25 r = f25_canon(f25_mul(ld_f25(scratch + row, npad), zi));
+    out[2 * row] = make_uint4(r.v[0] & ~zero, r.v[1] & ~zero, r.v[2] & ~zero, r.v[3] & ~zero);
+    out[2 * row + 1] = make_uint4(r.v[4] & ~zero, r.v[5] & ~zero, r.v[6] & ~zero, r.v[7] & ~zero);
+  }
+};
+
+// ---------------------------------------------------------------- GFp25519.add/sub/mul/sqr/inv on 32-byte rows
+// (fields.py:267-362; the GFp25519 column of compare.py:14-49 compare_fields).  Any 256-bit input (the reference reduces ints
+// mod p), canonical little-endian output.
+enum { FQ_F25OP_MUL = 0, FQ_F25OP_SQR = 1, FQ_F25OP_INV = 2, FQ_F25OP_ADD = 3, FQ_F25OP_SUB = 4 };
+FQ_FN f25 f25_from_words(const u32* w) { f25 r; FQ_UNROLL for (int i = 0; i < 8; i++) r.v[i] = w[i]; return r; }
+template <int OP> FQ_FN void row_f25_op(const u32* a, const u32* b, u32* out) {
+  const f25 x = f25_from_words(a);
+  f25 r;
+  if (OP == FQ_F25OP_MUL) r = f25_mul(x, f25_from_words(b));
+  else if (OP == FQ_F25OP_ADD) r = f25_add(x, f25_from_words(b));
+  else if (OP == FQ_F25OP_SUB) r = f25_sub(x, f25_from_words(b));
+  else if (OP == FQ_F25OP_SQR) r = f25_sqr(x);
+  else r = f25_inv(x);
+  r = f25_canon(r);
+  FQ_UNROLL
+  for (int i = 0; i < 8; i++) out[i] = r.v[i];
+}
+// GFp25519.inv for FQ_BATCHINV_ROWS rows per thread with one z^(p-2) chain; inv(0) = 0 as the reference's chain gives
+struct F25InvIO {
+  const uint4* a; uint4* out; size_t n, t, stride;
+  FQ_MFN f25 z(int j, u32& zero) const {
+    const size_t row = t + (size_t)j * stride;
+    f25 v = f25_small(1);
+    if (row < n) v = ld_f25(a + 2 * row, 1);
+    return f25_one_if_zero(v, zero);
+  }
+  FQ_MFN void park(int j, const f25& acc) const {
+    const size_t row = t + (size_t)j * stride;
+    if (row < n) st_f25(out + 2 * row, 1, acc);
+  }
+  FQ_MFN f25 parked(int j) const {
+    const size_t row = t + (size_t)j * stride;
+    return row < n ? ld_f25(out + 2 * row, 1) : f25_small(1);
+  }
+  FQ_MFN void emit(int j, const f25& zi, u32 zero) const {
+    const size_t row = t + (size_t)j * stride;
+    if (row >= n) return;
+    f25 r = f25_canon(zi);
     out[2 * row] = make_uint4(r.v[0] & ~zero, r.v[1] & ~zero, r.v[2] & ~zero, r.v[3] & ~zero);
     out[2 * row + 1] = make_uint4(r.v[4] & ~zero, r.v[5] & ~zero, r.v[6] & ~zero, r.v[7] & ~zero);
   }

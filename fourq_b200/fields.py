@@ -126,6 +126,43 @@ class GFp:
         return _select("fq_fp_select", 16, c, x, y, ndev)
 
 
+def _f25(op, a, b, ndev):
+    a = _lib.rows(a, 32, "a")
+    if b is not None:
+        b = _lib.rows(b, 32, "b")
+        if a.shape != b.shape:
+            raise ValueError("operands must have the same shape")
+    out = np.empty_like(a)
+    _lib.check(_lib.lib().fq_fp25519_op(_lib.FPOP[op], _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.shape[0], ndev))
+    return out
+
+
+class GFp25519:
+    """Static methods named after fields.py GFp25519.* (the comparison field of compare.py:14-49); an element is a 32-byte
+    little-endian row, arrays are (N, 32) uint8.  Any 256-bit input is accepted (the reference reduces ints mod p), results
+    are canonical.  cswap is X25519's ladder step and lives inside the x25519 kernel."""
+
+    @staticmethod
+    def add(x, y, ndev=1):       # fields.py:267-270
+        return _f25("add", x, y, ndev)
+
+    @staticmethod
+    def sub(x, y, ndev=1):       # fields.py:273-276
+        return _f25("sub", x, y, ndev)
+
+    @staticmethod
+    def mul(x, y, ndev=1):       # fields.py:279-282
+        return _f25("mul", x, y, ndev)
+
+    @staticmethod
+    def sqr(x, ndev=1):          # fields.py:285-288
+        return _f25("sqr", x, None, ndev)
+
+    @staticmethod
+    def inv(x, ndev=1):          # fields.py:293-362
+        return _f25("inv", x, None, ndev)
+
+
 def pack(pairs):
     """[(re, im), ...] Python ints -> (N, 32) uint8 rows (fields.py:125-126 packing of each half)."""
     out = np.empty((len(pairs), 32), np.uint8)

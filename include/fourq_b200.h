@@ -110,6 +110,12 @@ FQ_API int fq_fp2_select(const uint8_t* c, const uint8_t* x, const uint8_t* y, u
 #define FQ_FP_INVSQRT 6
 FQ_API int fq_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
 
+/* ---- GF(2^255-19) field ops on 32-byte rows (little-endian 256-bit values): fields.py GFp25519.add :267, sub :273, mul :279,
+ * sqr :285, inv :293-362 -- the GFp25519 column of compare.py:14-49 (compare_fields).  op is FQ_FP_MUL, _SQR, _INV, _ADD or
+ * _SUB; a, b, out are (n,32); b is ignored by the unary ops (may be NULL).  Inputs may be any 256-bit value (the reference
+ * reduces ints mod p); outputs are canonical; inv(0) = 0 as the reference's chain gives. */
+FQ_API int fq_fp25519_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, int ndev);
+
 /* ---- point codec: curve4q.py decode :49-96 (enc (n,32) -> xy (n,64) + status), encode :41-46 (xy -> enc).
  * Unlike the reference, decode does not modify its input. */
 FQ_API int fq_decode(const uint8_t* enc, uint8_t* xy, uint8_t* status, size_t n, int ndev);
@@ -178,6 +184,7 @@ FQ_API int fq_device_numa_node(int dev);          /* the NUMA node of a GPU, -1 
 #define FQ_DEVOP_FP2_SELECT 8  /* a = x, b = y, c = cond (1 byte per row), out: fq_dev_run3 */
 #define FQ_DEVOP_FP_SELECT 9   /* the same on 16-byte rows */
 #define FQ_DEVOP_FP_BASE 32    /* FQ_DEVOP_FP_BASE + FQ_FP_*: GF(p) ops on 16-byte rows, a (, b), out */
+#define FQ_DEVOP_F25519_BASE 48 /* FQ_DEVOP_F25519_BASE + FQ_FP_MUL/_SQR/_INV/_ADD/_SUB: GF(2^255-19) ops on 32-byte rows */
 #define FQ_DEVOP_DECODE 16     /* a = enc, out = xy, status */
 #define FQ_DEVOP_ENCODE 17     /* a = xy, out = enc */
 #define FQ_DEVOP_ON_CURVE 30      /* a = xy, out = ok (1 byte per row) */

@@ -692,6 +692,26 @@ def fp25519_inv(z):          # fields.py:293-362 computes z^(p-2); any chain giv
     return pow(z, P25519 - 2, P25519)
 
 
+def row_f25519(op, a, b=None):
+    """GFp25519.add/sub/mul/sqr/inv (fields.py:267-362) on 32-byte little-endian rows; inputs are arbitrary 256-bit ints as in the
+    reference (it reduces mod p), the output is the canonical value."""
+    x = int.from_bytes(a, "little")
+    y = int.from_bytes(b, "little") if b is not None else None
+    if op == "add":
+        r = (x + y) % P25519
+    elif op == "sub":
+        r = (x - y) % P25519
+    elif op == "mul":
+        r = (x * y) % P25519
+    elif op == "sqr":
+        r = (x * x) % P25519
+    elif op == "inv":
+        r = fp25519_inv(x)
+    else:
+        raise ValueError(op)
+    return r.to_bytes(32, "little")
+
+
 def x25519_ladder(k, u):     # curve25519.py:43-80 with bits = 255, a24 = 121665
     p = P25519
     x1, x2, z2, x3, z3, swap = u, 1, 0, u, 1, 0

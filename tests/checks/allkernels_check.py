@@ -50,6 +50,10 @@ assert (fq.GFp.select(c, a[:, :16], b[:, :16]) == np.where(c.reshape(-1, 1) == 1
 a2 = a.copy(); a2[::5, 16:] = 0
 assert [bytes(r) for r in fq.GFp2.invsqrt(a2)] == [O.row_fp2("invsqrt", bytes(r)) for r in a2]   # k_fp2_invsqrt
 assert (fq.curve4q.PointOnCurve(xy) == (st == 0)).all()                                          # k_on_curve (failed rows are zero-filled: off the curve)
+for op in ("mul", "add", "sub"):
+    assert [bytes(r) for r in getattr(fq.GFp25519, op)(a, b)[:200]] == [O.row_f25519(op, bytes(a[i]), bytes(b[i])) for i in range(200)]    # k_f25_op
+for op in ("sqr", "inv"):
+    assert [bytes(r) for r in getattr(fq.GFp25519, op)(a2)] == [O.row_f25519(op, bytes(r)) for r in a2]                                   # k_f25_inv_batched
 u = fq.x25519(k, a)                          # k_x25519 + k_x25519_finish
 assert [bytes(r) for r in u[:64]] == [O.x25519(bytes(k[i]), bytes(a[i])) for i in range(64)]
 print("allkernels_check: all kernels ran, outputs match the C oracle")

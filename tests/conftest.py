@@ -21,4 +21,4 @@ def load_golden(name):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {n[:-5]: load_golden(n) for n in ("fields.json", "fp.json", "codec.json", "mul.json", "endo.json", "x25519.json", "cfg1.json", "select.json")}
+    return {n[:-5]: load_golden(n) for n in ("fields.json", "fp.json", "codec.json", "mul.json", "endo.json", "x25519.json", "cfg1.json", "select.json", "f25519.json")}

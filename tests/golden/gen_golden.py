@@ -309,6 +309,22 @@ def main():
         sel["fp2_invsqrt"].append([f2b(a), f2b(GFp2.invsqrt(a))])
     dump("select.json", sel)
 
+    # ------------------------------------------------------------------ GFp25519 field ops (fields.py:267-362), compare_fields' other column
+    rng = random.Random(0xF25519)
+    GF25 = fields.GFp25519
+    q = fields.p25519
+    le32 = lambda v: int(v).to_bytes(32, "little").hex()
+    edge25 = [0, 1, 2, 19, 38, q - 1, q, q + 1, 2 * q, 2 * q + 1, 2 * q + 37, 1 << 255, (1 << 256) - 1, (1 << 255) - 1, 1 << 128, (1 << 128) - 1]
+    vals = edge25 + [rng.getrandbits(256) for _ in range(48)]
+    f25 = {"add": [], "sub": [], "mul": [], "sqr": [], "inv": []}
+    for i, x in enumerate(vals):
+        for y in (vals[(i * 7 + 3) % len(vals)], edge25[i % len(edge25)]):
+            for op in ("add", "sub", "mul"):
+                f25[op].append([le32(x), le32(y), le32(getattr(GF25, op)(x, y))])
+        f25["sqr"].append([le32(x), le32(GF25.sqr(x))])
+        f25["inv"].append([le32(x), le32(GF25.inv(x))])
+    dump("f25519.json", f25)
+
 
 if __name__ == "__main__":
     main()

@@ -207,6 +207,31 @@ int sim_x25519_batched(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t 
   }
   return 0;
 }
+// k_f25_op / k_f25_inv_batched (x25519.cu): GFp25519 ops on 32-byte rows, op = FQ_F25OP_*
+int sim_f25_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u32 wa[8], wb[8] = {0}, wo[8]; memcpy(wa, a + 32 * i, 32);
+    if (b) memcpy(wb, b + 32 * i, 32);
+    switch (op) {
+      case FQ_F25OP_MUL: row_f25_op<FQ_F25OP_MUL>(wa, wb, wo); break;
+      case FQ_F25OP_SQR: row_f25_op<FQ_F25OP_SQR>(wa, wb, wo); break;
+      case FQ_F25OP_INV: row_f25_op<FQ_F25OP_INV>(wa, wb, wo); break;
+      case FQ_F25OP_ADD: row_f25_op<FQ_F25OP_ADD>(wa, wb, wo); break;
+      case FQ_F25OP_SUB: row_f25_op<FQ_F25OP_SUB>(wa, wb, wo); break;
+      default: return 1;
+    }
+    memcpy(out + 32 * i, wo, 32);
+  }
+  return 0;
+}
+int sim_f25_inv_batched(const uint8_t* a, uint8_t* out, size_t n, int rows_per_thread) {
+  const size_t groups = (n + rows_per_thread - 1) / rows_per_thread, threads = (groups + 63) / 64 * 64;
+  for (size_t t = 0; t < threads; t++) {
+    F25InvIO io; io.a = reinterpret_cast<const uint4*>(a); io.out = reinterpret_cast<uint4*>(out); io.n = n; io.stride = threads; io.t = t;
+    batch_invert<F25Ops>(io, rows_per_thread);
+  }
+  return 0;
+}
 // digits of the recoding: idx[62], neg[62] for i = 61..0 (in pop order), plus the reduced odd scalar (32 bytes)
 int sim_recode(const uint8_t* k, uint8_t* idx, uint8_t* neg, uint8_t* reduced) {
   u32 wk[8]; memcpy(wk, k, 32);

@@ -24,6 +24,8 @@ int sim_dh_endo_affine(const uint8_t* k, const uint8_t* xy, uint8_t* out, uint8_
 int sim_fixed_base(int dh, const uint8_t* k, uint8_t* out, uint8_t* status, size_t n);
 int sim_comb(int dh, const uint8_t* k, uint8_t* out, uint8_t* status, size_t n);
 int sim_x25519_batched(const uint8_t* k, const uint8_t* u, uint8_t* out, size_t n, int rows_per_thread);
+int sim_f25_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+int sim_f25_inv_batched(const uint8_t* a, uint8_t* out, size_t n, int rows_per_thread);
 }
 typedef const uint8_t* cu8;
 typedef uint8_t* u8;
@@ -81,6 +83,10 @@ cudaError_t fqk_comb(int dh, int, const void*, const void* k, void* out, void* s
 size_t fqk_x25519_scratch_bytes(size_t n) { return (n + 127) / 128 * 128 * 64; }
 cudaError_t fqk_x25519(const void* k, const void* u, void* out, size_t n, void* scratch, cudaStream_t s) {
   mock_stream_enqueue(s, [=] { memset(scratch, 0x11, fqk_x25519_scratch_bytes(n)); sim_x25519_batched((cu8)k, (cu8)u, (u8)out, n, 16); });
+  return cudaSuccess;
+}
+cudaError_t fqk_f25_op(int op, const void* a, const void* b, void* out, size_t n, cudaStream_t s) {
+  mock_stream_enqueue(s, [=] { if (op == 2) sim_f25_inv_batched((cu8)a, (u8)out, n, 16); else sim_f25_op(op, (cu8)a, (cu8)b, (u8)out, n); });
   return cudaSuccess;
 }
 cudaError_t fqk_imad_peak(int, void*, int, int, cudaStream_t) { return cudaSuccess; }

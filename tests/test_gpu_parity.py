@@ -557,6 +557,38 @@ def test_fp2_inv_shared_inversion_with_zero_rows(fq):
         assert (got[(a == 0).all(axis=1)] == 0).all()
 
 
+def test_gfp25519_field_ops_golden_random_and_identities(fq, golden):
+    """fq_fp25519_op (fields.py:267-362 GFp25519.add/sub/mul/sqr/inv, compare.py:14-49's other column): the reference's vectors,
+    random unreduced rows against the oracle, zeros in every disguise through the shared inversion, and x * inv(x) == 1 at size."""
+    g = golden["f25519"]
+    for op in ("add", "sub", "mul"):
+        rows = g[op]
+        assert hexrows(getattr(fq.GFp25519, op)(R([H(r[0]) for r in rows]), R([H(r[1]) for r in rows]))) == [r[2] for r in rows], op
+    for op in ("sqr", "inv"):
+        rows = g[op]
+        assert hexrows(getattr(fq.GFp25519, op)(R([H(r[0]) for r in rows]))) == [r[1] for r in rows], op
+    rng = np.random.default_rng(2519)
+    q = O.P25519
+    for n in (1, 17, 4099):
+        a = rng.integers(0, 256, (n, 32), np.uint8); b = rng.integers(0, 256, (n, 32), np.uint8)
+        a[rng.random(n) < 0.1] = 0
+        a[rng.random(n) < 0.05] = np.frombuffer(q.to_bytes(32, "little"), np.uint8)
+        a[rng.random(n) < 0.05] = np.frombuffer((2 * q).to_bytes(32, "little"), np.uint8)
+        for op in ("add", "sub", "mul"):
+            assert [bytes(r) for r in getattr(fq.GFp25519, op)(a, b)] == [O.row_f25519(op, bytes(x), bytes(y)) for x, y in zip(a, b)], op
+        for op in ("sqr", "inv"):
+            assert [bytes(r) for r in getattr(fq.GFp25519, op)(a)] == [O.row_f25519(op, bytes(x)) for x in a], op
+    n = (1 << 20) + 5
+    a = rng.integers(0, 256, (n, 32), np.uint8)
+    one = np.zeros(32, np.uint8); one[0] = 1
+    assert (fq.GFp25519.mul(a, fq.GFp25519.inv(a)) == one).all()
+    assert (fq.GFp25519.sub(fq.GFp25519.add(a, a[::-1].copy()), a[::-1].copy()) == fq.GFp25519.add(a, np.zeros_like(a))).all()
+    assert (fq.GFp25519.sqr(a) == fq.GFp25519.mul(a, a)).all()
+    with pytest.raises(fq.FourQError):
+        from fourq_b200 import _lib
+        _lib.check(_lib.lib().fq_fp25519_op(6, _lib.ptr(a), None, _lib.ptr(a), 4, 1))
+
+
 def test_pageable_and_pinned_paths_agree_over_many_chunks(fq):
     """The host engine's staging of pageable inputs/outputs (capi.cu feeder / drainer) against page-locked buffers, on a batch that
     spans several ramped chunks; also rejects a device pointer as a host buffer."""

@@ -127,6 +127,23 @@ def test_three_input_select_through_the_engine(eng):
     assert (out16 == np.where(c.reshape(-1, 1) == 1, x16, y16)).all()
 
 
+def test_gfp25519_ops_through_the_engine(eng):
+    """fq_fp25519_op: binary, unary and the batched inversion (whose kernel parks prefixes in the output buffer) sliced over devices."""
+    from oracle import fourq_oracle as O
+    rng = np.random.default_rng(8)
+    n = 3001
+    a = rng.integers(0, 256, (n, 32), np.uint8); b = rng.integers(0, 256, (n, 32), np.uint8)
+    a[5] = 0; a[6] = np.frombuffer(O.P25519.to_bytes(32, "little"), np.uint8)
+    for op, code, binary in (("mul", 0, True), ("sqr", 1, False), ("inv", 2, False), ("add", 3, True), ("sub", 4, True)):
+        out = np.full_like(a, 0xEE)
+        assert eng.fq_fp25519_op(code, P(a), P(b) if binary else None, P(out), n, 3) == 0, eng.fq_last_error()
+        idx = list(range(0, n, 97)) + [5, 6, n - 1]
+        for i in idx:
+            assert bytes(out[i]) == O.row_f25519(op, bytes(a[i]), bytes(b[i]) if binary else None), (op, i)
+    assert eng.fq_fp25519_op(5, P(a), None, P(out), n, 1) != 0          # neg / invsqrt do not exist in GFp25519
+    assert eng.mock_violations() == 0
+
+
 def test_sliced_pinned_allocation_is_page_locked_and_freed(eng, sim):
     """fq_host_alloc_sliced: the NUMA placement is best effort (nothing to observe on this box), but the array must be
     page-locked over its whole length, usable by a multi-GPU call without staging, and released by fq_host_free."""

@@ -421,3 +421,35 @@ def test_x25519_shared_inversion(sim, golden):
     for rpt in (1, 16):
         assert sim.sim_x25519_batched(_p(k), _p(u), _p(out), ctypes.c_size_t(len(rows)), rpt) == 0
         assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[2] for r in rows]
+
+
+F25OP = {"mul": 0, "sqr": 1, "inv": 2, "add": 3, "sub": 4}
+
+
+def test_gfp25519_field_ops_golden_and_batched_inversion(sim, golden):
+    """x25519.cuh row_f25_op / F25InvIO against vectors produced by the reference's GFp25519.add/sub/mul/sqr/inv (unreduced operands,
+    p, 2p, 2^256 - 1 among them); the inversion also through the shared chain with zeros (0, p, 2p) in every group size."""
+    g = golden["f25519"]
+    for op in ("add", "sub", "mul"):
+        rows = g[op]
+        a = _rows([H(r[0]) for r in rows]); b = _rows([H(r[1]) for r in rows]); out = np.zeros_like(a)
+        assert sim.sim_f25_op(F25OP[op], _p(a), _p(b), _p(out), ctypes.c_size_t(len(rows))) == 0
+        assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[2] for r in rows], op
+    for op in ("sqr", "inv"):
+        rows = g[op]
+        a = _rows([H(r[0]) for r in rows]); out = np.zeros_like(a)
+        assert sim.sim_f25_op(F25OP[op], _p(a), None, _p(out), ctypes.c_size_t(len(rows))) == 0
+        assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[1] for r in rows], op
+    rows = g["inv"]
+    a = _rows([H(r[0]) for r in rows])
+    for rpt in (1, 4, 16, 32):
+        out = np.full_like(a, 0xEE)
+        assert sim.sim_f25_inv_batched(_p(a), _p(out), ctypes.c_size_t(len(rows)), rpt) == 0
+        assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[1] for r in rows], rpt
+    rng = random.Random(2519)
+    q = O.P25519
+    for n in (1, 63, 65, 1000):
+        A = [rng.choice([0, q, 2 * q, 1, q - 1, rng.getrandbits(256), rng.getrandbits(256)]).to_bytes(32, "little") for _ in range(n)]
+        a = _rows(A); out = np.full_like(a, 0xEE)
+        assert sim.sim_f25_inv_batched(_p(a), _p(out), ctypes.c_size_t(n), 16) == 0
+        assert [bytes(out[32 * i:32 * i + 32]) for i in range(n)] == [O.row_f25519("inv", x) for x in A]

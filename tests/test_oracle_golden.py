@@ -154,6 +154,17 @@ def test_endo_pieces(golden):
         assert "".join(map(str, gs)) == s and "".join(map(str, gd)) == d
 
 
+def test_gfp25519_field_ops(golden):
+    """fields.py:267-362 GFp25519.add/sub/mul/sqr/inv, unreduced 256-bit operands included."""
+    g = golden["f25519"]
+    for op in ("add", "sub", "mul"):
+        for a, b, out in g[op]:
+            assert O.row_f25519(op, H(a), H(b)).hex() == out
+    for op in ("sqr", "inv"):
+        for a, out in g[op]:
+            assert O.row_f25519(op, H(a)).hex() == out
+
+
 def test_x25519(golden):
     for k, u, out in golden["x25519"]["x25519"]:
         assert O.x25519(H(k), H(u)).hex() == out

@@ -6,7 +6,8 @@
     python tools/ncu_kernels_opmix.py gpurun_out/compare.ncu-rep 65536 > profiles/rNN_compare_opmix.json)
 
 Three tables, as compare.py prints them (compare.py:14-49, :51-169, :171-219):
-  1. time for N field operations in GF(p^2) (add, mul, sqr, inv): kernel time with device-resident rows, L2 flushed;
+  1. time for N field operations (add, mul, sqr, inv) in GF(p^2) and in GF(2^255-19): kernel time with device-resident rows,
+     L2 flushed;
   2. field-operation counts M / S / A / I per operation -- the reference's own counters, read from tests/golden/opcounts.json
      (written by tests/golden/gen_opcounts.py from the reference's code) -- next to the 32x32->64 multiply-adds that count
      implies under the limb model of SURVEY 8d (GF(p^2) M = 48, S = 32; GF(p) M = 16, S = 10) and, when an ncu capture is
@@ -116,14 +117,14 @@ def main():
     print("fourq_b200 compare (batched impl/compare.py), %d rows per batch, table selection: %s" % (n, "strict scan" if fq.get_select_mode() else "masked loads"))
     print()
     # ---- 1. field operations (compare.py:14-49)
-    print("===== Time for %d field operations (GF(p^2) rows, kernel time, device-resident) =====" % n)
+    print("===== Time for %d field operations (32-byte rows, kernel time, device-resident) =====" % n)
     print()
-    print("%-5s %10s %14s" % ("Op", "GFp2", "ops/s"))
+    print("%-5s %10s %10s %14s %14s" % ("Op", "GFp2", "GFp25519", "GFp2 ops/s", "GFp25519 ops/s"))
+    # compare.py:15-17: one corpus of 256-bit values, read as a GF(p^2) pair and as a GF(2^255-19) element
     a = fqdev.DeviceBuffer.from_host(0, rng.integers(0, 256, (n, 32), np.uint8)); b = fqdev.DeviceBuffer.from_host(0, rng.integers(0, 256, (n, 32), np.uint8))
     for name in ("add", "mul", "sqr", "inv"):
-        ms = best_ms("fp2_" + name, a, b if name in ("add", "mul") else None, dout, None, n)
-        print("%-5s %8.4fms %14.4g" % (name, ms, n / ms * 1e3))
-    print("(GF(2^255-19) field operations are not exposed: X25519 is a parity/throughput comparison kernel only)")
+        ms = [best_ms(f + name, a, b if name in ("add", "mul") else None, dout, None, n) for f in ("fp2_", "f25519_")]
+        print("%-5s %8.4fms %8.4fms %14.4g %14.4g" % (name, ms[0], ms[1], n / ms[0] * 1e3, n / ms[1] * 1e3))
     print()
     print_counts(opmix)
     # ---- 3. DH timing (compare.py:171-219)
