@@ -22,3 +22,25 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return {n[:-5]: load_golden(n) for n in ("fields.json", "fp.json", "codec.json", "mul.json", "endo.json", "x25519.json", "cfg1.json", "select.json", "f25519.json")}
+
+
+# The known-answer vectors of the reference's own X25519 self-test (impl/curve25519.py:96-107 rfc-0 / rfc-1, :131-149 test_dh;
+# RFC 7748 sections 5.2 and 6.1): (k, u, x25519(k, u)) as hex.  The iterated vector (:109-124) is run by the tests themselves.
+_A = "77076d0a7318a57d3c16c17251b26645df4c2f87ebc0992ab177fba51db92c2a"
+_KA = "8520f0098930a754748b7ddcb43ef75a0dbf3a0d26381af4eba4a98eaa9b4e6a"
+_B = "5dab087e624a8a4b79e17f8b83800ee66f3bb1292618b6fd1c2f8b27ff88e0eb"
+_KB = "de9edb7d7b7dc1b4d35b61c2ece435373f8343c85b78674dadfc7e146f882b4f"
+_K = "4a5d9d5ba4ce2de1728e3bf480350f25e07e21c947d19e3376f09b3c1e161742"
+_NINE = "09" + "00" * 31
+X25519_KAT = [
+    ("a546e36bf0527c9d3b16154b82465edd62144c0ac1fc5a18506a2244ba449ac4", "e6db6867583030db3594c1a424b15f7c726624ec26b3353b10a903a6d0ab1c4c",
+     "c3da55379de9c6908e94ea4df28d084f32eccf03491c71f754b4075577a28552"),
+    ("4b66e9d4d1b4673c5ad22691957d6af5c11b6421e0ea01d42ca4169e7918ba0d", "e5210f12786811d3f4b7959d0538ae2c31dbe7106fc03c3efc4cd549c715a493",
+     "95cbde9476e8907d7aade45cb4b873f88b595a68799fa152e6f8f7647aac7957"),
+    (_A, _NINE, _KA), (_B, _NINE, _KB), (_A, _KB, _K), (_B, _KA, _K),
+]
+
+
+@pytest.fixture(scope="session")
+def x25519_kat():
+    return X25519_KAT

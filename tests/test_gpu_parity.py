@@ -196,10 +196,12 @@ def test_strict_mode_raises_reference_messages(fq, golden):
         fq.DH_base(fq.curve4q.pack_scalars([O.N]), strict=True)
 
 
-def test_x25519_golden_and_rfc(fq, golden):
+def test_x25519_golden_and_rfc(fq, golden, x25519_kat):
     rows = golden["x25519"]["x25519"]
     got = fq.x25519(R([H(r[0]) for r in rows]), R([H(r[1]) for r in rows]))
     assert hexrows(got) == [r[2] for r in rows]
+    kat = x25519_kat                              # the reference's own known answers: curve25519.py:96-107 (rfc-0/1), :131-149 (test_dh)
+    assert hexrows(fq.x25519(R([H(r[0]) for r in kat]), R([H(r[1]) for r in kat]))) == [r[2] for r in kat]
     k = u = R([bytes([9] + [0] * 31)])
     for i in range(1000):                        # RFC 7748 5.2, curve25519.py:104-124
         k, u = fq.x25519(k, u), k

@@ -212,11 +212,18 @@ def test_dh_golden(sim, golden):
         assert (int(st[i]), bytes(out[64 * i:64 * i + 64]).hex()) == (want_st, want), (kk, pp)
 
 
-def test_x25519_golden_and_rfc(sim, golden):
+def test_x25519_golden_and_rfc(sim, golden, x25519_kat):
     rows = golden["x25519"]["x25519"]
     k = _rows([H(r[0]) for r in rows]); u = _rows([H(r[1]) for r in rows]); out = np.zeros(32 * len(rows), np.uint8)
     sim.sim_x25519(_p(k), _p(u), _p(out), ctypes.c_size_t(len(rows)))
     assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(rows))] == [r[2] for r in rows]
+    # the reference's own known answers (curve25519.py:96-107, :131-149), per row and through the shared inversion
+    kat = x25519_kat
+    k = _rows([H(r[0]) for r in kat]); u = _rows([H(r[1]) for r in kat])
+    for fn in (lambda o: sim.sim_x25519(_p(k), _p(u), _p(o), ctypes.c_size_t(len(kat))),
+               lambda o: sim.sim_x25519_batched(_p(k), _p(u), _p(o), ctypes.c_size_t(len(kat)), 16)):
+        out = np.zeros(32 * len(kat), np.uint8); fn(out)
+        assert [bytes(out[32 * i:32 * i + 32]).hex() for i in range(len(kat))] == [r[2] for r in kat]
     # RFC 7748 5.2 iteration vector (curve25519.py:104-124): 1 and 1000 iterations
     kk = uu = bytes([9] + [0] * 31)
     for i in range(1000):

@@ -168,7 +168,9 @@ def test_gfp25519_field_ops(golden):
 def test_x25519(golden):
     for k, u, out in golden["x25519"]["x25519"]:
         assert O.x25519(H(k), H(u)).hex() == out
-    # RFC 7748 5.2 vector, as in curve25519.py:97-102
-    assert O.x25519(H("a546e36bf0527c9d3b16154b82465edd62144c0ac1fc5a18506a2244ba449ac4"),
-                    H("e6db6867583030db3594c1a424b15f7c726624ec26b3353b10a903a6d0ab1c4c")).hex() == \
-        "c3da55379de9c6908e94ea4df28d084f32eccf03491c71f754b4075577a28552"
+
+
+def test_x25519_reference_self_test_vectors(x25519_kat):
+    """curve25519.py:96-107 (rfc-0, rfc-1) and :131-149 (test_dh: KA, KB and the shared K from both sides)."""
+    for k, u, out in x25519_kat:
+        assert O.x25519(H(k), H(u)).hex() == out
